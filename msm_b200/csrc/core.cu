@@ -1,0 +1,1132 @@
+// core.cu -- grid-level C ABI (msm_*): device state of a batch of streams and the fused pass sequences of one
+// MSM time step.  See include/msm_b200.h for the contract and DESIGN.md for the data layout.
+//
+// Device layout (n = size, C = n^dims cells, S = local streams, G = chunk_streams):
+//   X    [S][C] complex128   the ONE resident array per stream.  Between steps it holds psi_k (after the second
+//                            drift, simulation_object.rs:574); inside msm_step it is transformed in place
+//                            psi_k -> psi -> psi_k.  (The reference keeps psi, psi_k and phi: 3 arrays, :42-64.)
+//   T    [G][C] complex128   scratch for the out-of-place transform psi_k -> rho that feeds the dt potential
+//                            (the reference's `calculate_potential` at time t, :497) and for dumps.
+//   P    [ceil(G/2)][C] complex128   pair buffers: rho_a + i rho_b  ->  phi_a + i phi_b.
+//   dtab [S][n] complex128   per-axis drift factors n^(-1/2) exp(-i c_s (2 pi k_m)^2): exp(-i c k^2) is separable,
+//                            so the reference's 2 GiB `k_evolution` temporary (:504-514) becomes a 8 KiB table.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/msm_b200.h"
+#include "fft_pass.cuh"
+
+namespace msm {
+#define DECL(N) int launch_pass_##N(bool, int, int, const PassParams&, int, int, cudaStream_t);
+DECL(2) DECL(4) DECL(8) DECL(16) DECL(32) DECL(64) DECL(128) DECL(256) DECL(512) DECL(1024)
+#undef DECL
+
+pass_launcher_t get_pass_launcher(int n) {
+    switch (n) {
+#define C(N) case N: return launch_pass_##N;
+        C(2) C(4) C(8) C(16) C(32) C(64) C(128) C(256) C(512) C(1024)
+#undef C
+    }
+    return nullptr;
+}
+
+static int plan_T(int n) { return n >= 8 ? 8 : n; }
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_interleave(const double* __restrict__ re, const double* __restrict__ im, double2* __restrict__ out,
+                             long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = make_double2(re[i], im[i]);
+}
+__global__ void k_deinterleave(const double2* __restrict__ in, double* __restrict__ re, double* __restrict__ im,
+                               long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double2 v = in[i];
+        re[i] = v.x;
+        im[i] = v.y;
+    }
+}
+__global__ void k_extract(const double2* __restrict__ in, double* __restrict__ out, long long n, int comp) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double2 v = in[i];
+        out[i] = comp ? v.y : v.x;
+    }
+}
+// alias_out[s] = dv * sum_tiles partial[s][tile]    (fixed summation order: deterministic)
+__global__ void k_alias_reduce(const double* __restrict__ partial, double* __restrict__ out, int ntiles, double dv) {
+    __shared__ double sh[256];
+    const int s = blockIdx.x;
+    const double* p = partial + (long long)s * ntiles;
+    double a = 0.0;
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) a += p[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[s] = sh[0] * dv;
+}
+// k^2 from indices, same expression as the pass kernels (parity with spec_grid, utils/fft.rs:123-161)
+__global__ void k_spec_grid(const double* __restrict__ ksq, double* __restrict__ out, int n, int dims, double four_pi2) {
+    long long total = 1;
+    for (int d = 0; d < dims; ++d) total *= n;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+         q += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)(q % n);
+        int c1 = dims >= 2 ? (int)((q / n) % n) : 0;
+        int c2 = dims >= 3 ? (int)(q / ((long long)n * n)) : 0;
+        double s = ksq[c0];
+        if (dims >= 2) s = s + ksq[c1];
+        if (dims >= 3) s = s + ksq[c2];
+        out[q] = s * four_pi2;
+    }
+}
+__global__ void k_scale_real(double2* __restrict__ a, long long n, double f) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double2 v = a[i];
+        v.x *= f;
+        v.y *= f;
+        a[i] = v;
+    }
+}
+
+// ---- on-device initial conditions (restates simulator/src/ics.rs) --------------------------
+// psi(i,j,k) = gx[k] * gy[j] * gz[i] * norm          (cold_gauss, ics.rs:24-162: separable, already normalised)
+__global__ void k_ic_separable(double2* __restrict__ psi, const double* __restrict__ g, int n, int dims, double norm) {
+    long long total = 1;
+    for (int d = 0; d < dims; ++d) total *= n;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+         q += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)(q % n);
+        int c1 = dims >= 2 ? (int)((q / n) % n) : 0;
+        int c2 = dims >= 3 ? (int)(q / ((long long)n * n)) : 0;
+        double v = g[c0];
+        if (dims >= 2) v = g[n + c1] * v;
+        if (dims >= 3) v = g[2 * n + c2] * v;
+        psi[q] = make_double2(v * norm, 0.0);
+    }
+}
+// spherical_tophat (ics.rs:165-280): sqrt(1 + delta / (1 + exp(slope (r/R - 1)))), un-normalised
+__global__ void k_ic_tophat(double2* __restrict__ psi, int n, int dims, double dx, double half, double radius,
+                            double delta, double slope) {
+    long long total = 1;
+    for (int d = 0; d < dims; ++d) total *= n;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+         q += (long long)gridDim.x * blockDim.x) {
+        int c0 = (int)(q % n);
+        int c1 = dims >= 2 ? (int)((q / n) % n) : -1;
+        int c2 = dims >= 3 ? (int)(q / ((long long)n * n)) : -1;
+        // reference loop order: x outermost (slowest NumPy axis), z innermost; the radius is symmetric
+        double a = (2.0 * c0 + 1.0) * dx / 2.0 - half;
+        double b = c1 >= 0 ? (2.0 * c1 + 1.0) * dx / 2.0 - half : 0.0;
+        double c = c2 >= 0 ? (2.0 * c2 + 1.0) * dx / 2.0 - half : 0.0;
+        double r;
+        if (dims == 3) r = sqrt(c * c + b * b + a * a);
+        else if (dims == 2) r = sqrt(b * b + a * a + 0.0);
+        else r = sqrt(a * a + 0.0 + 0.0);
+        double ramp = 1.0 / (1.0 + exp(slope * (r / radius - 1.0)));
+        psi[q] = make_double2(sqrt(1.0 + delta * ramp), 0.0);
+    }
+}
+__global__ void k_norm2_partial(const double2* __restrict__ a, long long n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double2 v = a[i];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                              uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+// sample_quantum_perturbation, Wigner / Husimi (ics.rs:560-646): psi = (psi sqrt(dV) + (N + iN) / div) / sqrt(dV)
+__global__ void k_sample_gauss(double2* __restrict__ psi, long long n, uint64_t seed, double sqrt_dv, double div) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        uint32_t c0 = (uint32_t)q, c1 = (uint32_t)((uint64_t)q >> 32), c2 = 0u, c3 = 0u;
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double u1 = u53(c0, c1), u2 = u53(c2, c3);
+        const double r = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincos(2.0 * 3.14159265358979323846 * u2, &sn, &cs);
+        double2 v = psi[q];
+        v.x = (v.x * sqrt_dv + (r * cs) / div) / sqrt_dv;
+        v.y = (v.y * sqrt_dv + (r * sn) / div) / sqrt_dv;
+        psi[q] = v;
+    }
+}
+}  // namespace msm
+
+using namespace msm;
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL through dlopen (only the coupled mode with nranks > 1 needs it)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid_t;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) return false;
+        GetUniqueId = (int (*)(nccl_uid_t*))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(void**, int, nccl_uid_t, int))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
+    }
+};
+NcclApi g_nccl;
+const int NCCL_DOUBLE = 8;  // ncclFloat64
+const int NCCL_SUM = 0;
+
+std::string g_create_error;
+}  // namespace
+
+struct ProfEvent {
+    cudaEvent_t a, b;
+    int key;
+    double bytes;
+};
+
+struct msm_ctx {
+    msm_config cfg;
+    int n = 0, dims = 0, S = 0, chunk = 0, T = 0;
+    long long C = 0;
+    cudaStream_t st = nullptr;
+    double2 *X = nullptr, *Tscr = nullptr, *P = nullptr, *tw = nullptr, *dtab = nullptr;
+    double2* h_dtab = nullptr;   // pinned
+    cudaEvent_t dtab_done = nullptr;
+    double* ksq = nullptr;
+    double* alias_partial = nullptr;
+    double* alias_out = nullptr;
+    double* h_scal = nullptr;    // pinned, 2*S doubles
+    unsigned long long* maxbits = nullptr;
+    double* scratch_small = nullptr;  // 4096 doubles
+    std::vector<char> in_k, has_psi;
+    std::vector<double> h_ksq;
+    double four_pi2 = 0, k2_max = 0, dv = 0;
+    int ntiles_last = 0;
+    uint64_t bytes = 0, launches = 0;
+    void* comm = nullptr;
+    // profiling
+    bool prof = false;
+    std::vector<ProfEvent> prof_pending;
+    std::vector<std::string> prof_names;
+    std::map<std::string, int> prof_index;
+    std::vector<msm_profile_record> prof_rec;
+    std::string err;
+    pass_launcher_t launcher = nullptr;
+};
+
+namespace {
+
+int fail(msm_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, MSM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct Geom {
+    int axis, tiles_inner, ntiles, lvalid;
+    long long outer, inner, lstride, astride;
+};
+Geom make_geom(const msm_ctx* c, int axis) {
+    Geom g{};
+    const int n = c->n, T = c->T;
+    g.axis = axis;
+    if (axis == 0) {
+        const long long nlines = c->C / n;
+        g.ntiles = (int)((nlines + T - 1) / T);
+        g.tiles_inner = g.ntiles;
+        g.inner = (long long)T * n;
+        g.outer = 0;
+        g.lstride = n;
+        g.astride = 1;
+        g.lvalid = (int)std::min<long long>(T, nlines);
+    } else if (axis == 1) {
+        g.tiles_inner = n / T;
+        g.ntiles = g.tiles_inner * (c->dims == 3 ? n : 1);
+        g.inner = T;
+        g.outer = (long long)n * n;
+        g.lstride = 1;
+        g.astride = n;
+        g.lvalid = T;
+    } else {
+        g.ntiles = (int)(((long long)n * n) / T);
+        g.tiles_inner = g.ntiles;
+        g.inner = T;
+        g.outer = 0;
+        g.lstride = 1;
+        g.astride = (long long)n * n;
+        g.lvalid = T;
+    }
+    return g;
+}
+
+const char* lop_name(int l) { return l == L_NONE ? "none" : l == L_DRIFT ? "drift" : "kick"; }
+const char* sop_name(int s) {
+    switch (s) {
+        case S_NONE: return "none";
+        case S_SCALE: return "scale";
+        case S_DRIFT: return "drift";
+        case S_DRIFT_ALIAS: return "drift+alias";
+        case S_RHO_KEEP: return "psi+rho";
+        case S_RHO_ONLY: return "rho";
+        case S_POISSON: return "poisson";
+        case S_MAX: return "max";
+    }
+    return "?";
+}
+
+double pass_bytes(const msm_ctx* c, int lop, int sop, int ns) {
+    double per = 16.0;                                   // read the line
+    if (lop == L_KICK) per += 8.0;                       // phi
+    if (sop != S_RHO_ONLY && sop != S_MAX) per += 16.0;  // write the line
+    if (sop == S_RHO_KEEP || sop == S_RHO_ONLY) per += 8.0;
+    return per * (double)c->C * ns;
+}
+
+int prof_key(msm_ctx* c, const std::string& name) {
+    auto it = c->prof_index.find(name);
+    if (it != c->prof_index.end()) return it->second;
+    int k = (int)c->prof_names.size();
+    c->prof_names.push_back(name);
+    c->prof_index[name] = k;
+    c->prof_rec.push_back(msm_profile_record{nullptr, 0, 0.0, 0.0});
+    return k;
+}
+
+struct ProfScope {
+    msm_ctx* c;
+    ProfEvent ev{};
+    bool on;
+    ProfScope(msm_ctx* c_, const std::string& name, double bytes) : c(c_), on(c_->prof) {
+        if (!on) return;
+        ev.key = prof_key(c, name);
+        ev.bytes = bytes;
+        cudaEventCreate(&ev.a);
+        cudaEventCreate(&ev.b);
+        cudaEventRecord(ev.a, c->st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(ev.b, c->st);
+        c->prof_pending.push_back(ev);
+    }
+};
+
+void prof_drain(msm_ctx* c) {
+    for (auto& e : c->prof_pending) {
+        cudaEventSynchronize(e.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        c->prof_rec[e.key].launches += 1;
+        c->prof_rec[e.key].ms_total += ms;
+        c->prof_rec[e.key].algorithmic_bytes += e.bytes;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    c->prof_pending.clear();
+}
+
+// what the passes of one transform do besides the FFT
+struct XformOps {
+    int lop_first = L_NONE, lop_each = L_NONE, sop_each = S_NONE, sop_last = S_NONE;
+    int gsz = 2;
+    int p_summed = 0, rho_accumulate = 0;
+    double rho_coef = 0, scale = 1, poisson_coef = 0;
+    const double* kick = nullptr;   // per local index
+    double2* pbuf = nullptr;
+    unsigned long long* maxbits = nullptr;
+};
+
+// d-dimensional transform of the streams ids[0..ns): first pass reads `src`, every pass writes `work`.
+int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2* src, int src_by_sid, double2* work,
+                  int work_by_sid, const XformOps& o) {
+    PassParams p{};
+    p.src_sstride = p.dst_sstride = ctx->C;
+    p.ns = ns;
+    p.gsz = o.gsz;
+    for (int i = 0; i < ns; ++i) p.sid[i] = ids[i];
+    p.n = ctx->n;
+    p.twiddle = ctx->tw;
+    p.dtab = ctx->dtab;
+    if (o.kick) for (int i = 0; i < ns; ++i) p.kick[i] = o.kick[i];
+    p.pbuf = o.pbuf ? o.pbuf : ctx->P;
+    p.p_gstride = ctx->C;
+    p.p_summed = o.p_summed;
+    p.rho_accumulate = o.rho_accumulate;
+    p.ksq = ctx->ksq;
+    p.four_pi2 = ctx->four_pi2;
+    p.alias_k2_thresh = ctx->k2_max * ctx->cfg.k2_cutoff;   // simulation_object.rs:1265
+    p.poisson_coef = o.poisson_coef;
+    p.rho_coef = o.rho_coef;
+    p.scale = o.scale;
+    p.alias_partial = ctx->alias_partial;
+    p.maxbits = o.maxbits ? o.maxbits : ctx->maxbits;
+    const int groups = (ns + o.gsz - 1) / o.gsz;
+    for (int k = 0; k < ctx->dims; ++k) {
+        const int axis = inv ? ctx->dims - 1 - k : k;
+        const Geom g = make_geom(ctx, axis);
+        const bool first = (k == 0), last = (k == ctx->dims - 1);
+        const int lop = (first && o.lop_first != L_NONE) ? o.lop_first : o.lop_each;
+        const int sop = last ? o.sop_last : o.sop_each;
+        p.src = first ? src : work;
+        p.src_by_sid = first ? src_by_sid : work_by_sid;
+        p.dst = work;
+        p.dst_by_sid = work_by_sid;
+        p.axis = axis;
+        p.tiles_inner = g.tiles_inner;
+        p.outer_stride = g.outer;
+        p.inner_stride = g.inner;
+        p.lstride = g.lstride;
+        p.astride = g.astride;
+        p.lvalid = g.lvalid;
+        p.ntiles = g.ntiles;
+        char nm[96];
+        snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s>", ctx->n, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop));
+        int rc;
+        {
+            ProfScope ps(ctx, nm, pass_bytes(ctx, lop, sop, ns));
+            rc = ctx->launcher(inv, lop, sop, p, g.ntiles, groups, ctx->st);
+        }
+        ctx->launches++;
+        if (rc == -1) return fail(ctx, MSM_E_ARG, std::string("no kernel instance for ") + nm);
+        if (rc != 0) return fail(ctx, MSM_E_CUDA, std::string(nm) + ": " + cudaGetErrorString((cudaError_t)rc));
+    }
+    return MSM_OK;
+}
+
+int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
+
+int ensure_kspace(msm_ctx* ctx, const std::vector<int>& ids) {
+    std::vector<int> todo;
+    for (int s : ids) {
+        if (!ctx->has_psi[s]) return fail(ctx, MSM_E_STATE, "stream has no wavefunction (call msm_set_psi first)");
+        if (!ctx->in_k[s]) todo.push_back(s);
+    }
+    for (size_t i = 0; i < todo.size(); i += ctx->chunk) {
+        const int ns = (int)std::min<size_t>(ctx->chunk, todo.size() - i);
+        XformOps o;
+        o.sop_each = o.sop_last = S_SCALE;
+        o.scale = 1.0 / sqrt((double)ctx->n);   // n^(-dims/2) over dims passes (utils/fft.rs:17)
+        int rc = run_transform(ctx, false, &todo[i], ns, ctx->X, 1, ctx->X, 1, o);
+        if (rc) return rc;
+    }
+    for (int s : todo) ctx->in_k[s] = 1;
+    return MSM_OK;
+}
+
+std::vector<int> active_list(const msm_ctx* ctx, const int32_t* active) {
+    std::vector<int> ids;
+    for (int s = 0; s < ctx->S; ++s)
+        if (!active || active[s]) ids.push_back(s);
+    return ids;
+}
+
+int allreduce_rho(msm_ctx* ctx) {
+    if (ctx->cfg.nranks <= 1) return MSM_OK;
+    ProfScope ps(ctx, "nccl_allreduce_rho", 0.0);
+    int rc = g_nccl.AllReduce(ctx->P, ctx->P, (size_t)(2 * ctx->C), NCCL_DOUBLE, NCCL_SUM, ctx->comm, ctx->st);
+    if (rc != 0)
+        return fail(ctx, MSM_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    return MSM_OK;
+}
+
+// Poisson solve in place on `nbuf` pair buffers starting at ctx->P:  phi = F^-1[ c/(k^2 n^d) F[rho] ]
+int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits) {
+    std::vector<int> ids(nbuf);
+    for (int i = 0; i < nbuf; ++i) ids[i] = i;
+    XformOps f;
+    f.gsz = 1;
+    f.sop_last = S_POISSON;
+    f.poisson_coef = ctx->cfg.poisson_coeff / pow((double)ctx->n, (double)ctx->dims);
+    int rc = run_transform(ctx, false, ids.data(), nbuf, ctx->P, 0, ctx->P, 0, f);
+    if (rc) return rc;
+    XformOps b;
+    b.gsz = 1;
+    b.sop_last = max_only ? S_MAX : S_NONE;
+    b.maxbits = maxbits;
+    return run_transform(ctx, true, ids.data(), nbuf, ctx->P, 0, ctx->P, 0, b);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* msm_version(void) { return "msm_b200 0.1 (sm_100a)"; }
+
+const char* msm_strerror(int code) {
+    switch (code) {
+        case MSM_OK: return "ok";
+        case MSM_E_ARG: return "bad argument";
+        case MSM_E_CUDA: return "CUDA error";
+        case MSM_E_NCCL: return "NCCL error";
+        case MSM_E_ALIASING: return "Fourier aliasing above threshold";
+        case MSM_E_NAN: return "NaN or Inf in grid";
+        case MSM_E_STATE: return "invalid call sequence";
+        case MSM_E_NOMEM: return "out of device memory";
+        case MSM_E_IO: return "I/O error";
+    }
+    return "unknown error";
+}
+
+int msm_nccl_unique_id(void* out128) {
+    if (!out128) return MSM_E_ARG;
+    if (!g_nccl.load()) return fail(nullptr, MSM_E_NCCL, "cannot load libnccl.so.2");
+    nccl_uid_t id;
+    if (g_nccl.GetUniqueId(&id) != 0) return fail(nullptr, MSM_E_NCCL, "ncclGetUniqueId failed");
+    memcpy(out128, &id, 128);
+    return MSM_OK;
+}
+
+const char* msm_last_error(const msm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int msm_create(const msm_config* cfg, msm_ctx** out) {
+    msm_ctx* ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, MSM_E_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(msm_config)) return fail(nullptr, MSM_E_ARG, "msm_config.struct_size mismatch");
+    if (cfg->dims < 1 || cfg->dims > 3) return fail(nullptr, MSM_E_ARG, "dims must be 1, 2 or 3");
+    const int n = cfg->size;
+    if (n < 2 || n > 1024 || (n & (n - 1))) return fail(nullptr, MSM_E_ARG, "size must be a power of two in [2, 1024]");
+    if (cfg->n_streams < 1) return fail(nullptr, MSM_E_ARG, "n_streams must be >= 1");
+    if (!(cfg->dx > 0.0)) return fail(nullptr, MSM_E_ARG, "dx must be positive");
+    if (cfg->coupling != MSM_COUPLING_INDEPENDENT && cfg->coupling != MSM_COUPLING_SUMMED)
+        return fail(nullptr, MSM_E_ARG, "unknown coupling mode");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MSM_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                             " (msm_b200 has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MSM_E_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, MSM_E_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MSM_E_CUDA, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, MSM_E_CUDA, cudaGetErrorString(e));
+
+    ctx = new msm_ctx();
+    ctx->cfg = *cfg;
+    ctx->n = n;
+    ctx->dims = cfg->dims;
+    ctx->S = cfg->n_streams;
+    ctx->T = plan_T(n);
+    ctx->C = 1;
+    for (int d = 0; d < cfg->dims; ++d) ctx->C *= n;
+    ctx->launcher = get_pass_launcher(n);
+    int chunk = cfg->chunk_streams > 0 ? cfg->chunk_streams : 8;
+    chunk = std::min(chunk, MAX_CHUNK);
+    chunk = std::min(chunk, ctx->S + (ctx->S & 1));
+    if (chunk > 1) chunk &= ~1;   // even, so that pairs never straddle chunks
+    chunk = std::max(chunk, 1);
+    ctx->chunk = chunk;
+    ctx->in_k.assign(ctx->S, 0);
+    ctx->has_psi.assign(ctx->S, 0);
+    ctx->four_pi2 = (2.0 * M_PI) * (2.0 * M_PI);
+    ctx->dv = pow(cfg->dx, (double)cfg->dims);   // dk = dx (simulation_object.rs:263), p_mass uses dk^dims (:1281-1285)
+
+    // k grid (utils/fft.rs:100-120) and k2_max = max(spec_grid) (simulation_object.rs:274)
+    ctx->h_ksq.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const double ii = (i < n / 2) ? (double)i : (double)(i - n);
+        const double k = ii / ((double)n * cfg->dx);
+        ctx->h_ksq[i] = k * k;
+    }
+    {
+        const double m = ctx->h_ksq[n / 2];
+        double s = m;
+        if (cfg->dims >= 2) s = s + m;
+        if (cfg->dims >= 3) s = s + m;
+        ctx->k2_max = s * ctx->four_pi2;
+    }
+
+    auto bail = [&](int code, const std::string& msg) {
+        std::string m = msg;
+        msm_destroy(ctx);
+        return fail(nullptr, code, m);
+    };
+#define CUC(call)                                                                      \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return bail(e_ == cudaErrorMemoryAllocation ? MSM_E_NOMEM : MSM_E_CUDA,    \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+    CUC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&ctx->dtab_done, cudaEventDisableTiming));
+    const size_t cb = sizeof(double2) * (size_t)ctx->C;
+    const int npair = (chunk + 1) / 2;
+    CUC(cudaMalloc(&ctx->X, cb * ctx->S));
+    CUC(cudaMalloc(&ctx->Tscr, cb * chunk));
+    CUC(cudaMalloc(&ctx->P, cb * npair));
+    CUC(cudaMalloc(&ctx->tw, sizeof(double2) * n));
+    CUC(cudaMalloc(&ctx->dtab, sizeof(double2) * n * ctx->S));
+    CUC(cudaMalloc(&ctx->ksq, sizeof(double) * n));
+    const Geom glast = make_geom(ctx, ctx->dims - 1);
+    ctx->ntiles_last = glast.ntiles;
+    CUC(cudaMalloc(&ctx->alias_partial, sizeof(double) * (size_t)ctx->S * glast.ntiles));
+    CUC(cudaMalloc(&ctx->alias_out, sizeof(double) * ctx->S));
+    CUC(cudaMalloc(&ctx->maxbits, sizeof(unsigned long long) * (ctx->S + 2)));
+    CUC(cudaMalloc(&ctx->scratch_small, sizeof(double) * 4096));
+    CUC(cudaMallocHost(&ctx->h_dtab, sizeof(double2) * n * ctx->S));
+    CUC(cudaMallocHost(&ctx->h_scal, sizeof(double) * 2 * (ctx->S + 2)));
+    ctx->bytes = cb * (ctx->S + chunk + npair) + sizeof(double2) * n * (ctx->S + 1) + sizeof(double) * n +
+                 sizeof(double) * (size_t)ctx->S * (glast.ntiles + 1) + 8 * (ctx->S + 2) + 8 * 4096;
+    CUC(cudaMemsetAsync(ctx->alias_out, 0, sizeof(double) * ctx->S, ctx->st));
+    CUC(cudaMemsetAsync(ctx->alias_partial, 0, sizeof(double) * (size_t)ctx->S * glast.ntiles, ctx->st));
+    {
+        std::vector<double2> tw(n);
+        for (int j = 0; j < n; ++j) {
+            // exact at the octants, libm elsewhere
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+            tw[j] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        CUC(cudaMemcpyAsync(ctx->tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->st));
+        CUC(cudaMemcpyAsync(ctx->ksq, ctx->h_ksq.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+        CUC(cudaStreamSynchronize(ctx->st));
+    }
+    if (cfg->coupling == MSM_COUPLING_SUMMED && cfg->nranks > 1) {
+        if (!cfg->nccl_unique_id) return bail(MSM_E_ARG, "nranks > 1 requires nccl_unique_id");
+        if (!g_nccl.load()) return bail(MSM_E_NCCL, "cannot load libnccl.so.2");
+        nccl_uid_t id;
+        memcpy(&id, cfg->nccl_unique_id, 128);
+        int rc = g_nccl.CommInitRank(&ctx->comm, cfg->nranks, id, cfg->rank);
+        if (rc != 0) return bail(MSM_E_NCCL, "ncclCommInitRank failed");
+    }
+#undef CUC
+    *out = ctx;
+    return MSM_OK;
+}
+
+void msm_destroy(msm_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    prof_drain(ctx);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    cudaFree(ctx->X);
+    cudaFree(ctx->Tscr);
+    cudaFree(ctx->P);
+    cudaFree(ctx->tw);
+    cudaFree(ctx->dtab);
+    cudaFree(ctx->ksq);
+    cudaFree(ctx->alias_partial);
+    cudaFree(ctx->alias_out);
+    cudaFree(ctx->maxbits);
+    cudaFree(ctx->scratch_small);
+    if (ctx->h_dtab) cudaFreeHost(ctx->h_dtab);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    if (ctx->dtab_done) cudaEventDestroy(ctx->dtab_done);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+int msm_device_bytes(const msm_ctx* ctx, uint64_t* bytes) {
+    if (!ctx || !bytes) return MSM_E_ARG;
+    *bytes = ctx->bytes;
+    return MSM_OK;
+}
+
+int msm_synchronize(msm_ctx* ctx) {
+    if (!ctx) return MSM_E_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+int msm_set_psi(msm_ctx* ctx, int32_t s, const double* psi) {
+    if (!ctx || !psi || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_set_psi: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->X + (size_t)s * ctx->C, psi, sizeof(double2) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->in_k[s] = 0;
+    ctx->has_psi[s] = 1;
+    return MSM_OK;
+}
+
+int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* im) {
+    if (!ctx || !re || !im || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_set_psi_planes: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    double* stage = reinterpret_cast<double*>(ctx->Tscr);   // 2*C doubles = one scratch slot
+    CU(cudaMemcpyAsync(stage, re, sizeof(double) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(stage + ctx->C, im, sizeof(double) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
+    k_interleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(stage, stage + ctx->C, ctx->X + (size_t)s * ctx->C, ctx->C);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->in_k[s] = 0;
+    ctx->has_psi[s] = 1;
+    return MSM_OK;
+}
+
+// psi of stream s into scratch slot 0 (or X itself when no transform has happened yet); returns the device pointer
+static int psi_on_device(msm_ctx* ctx, int s, const double2** out) {
+    if (!ctx->has_psi[s]) return fail(ctx, MSM_E_STATE, "stream has no wavefunction");
+    if (!ctx->in_k[s]) {
+        *out = ctx->X + (size_t)s * ctx->C;
+        return MSM_OK;
+    }
+    XformOps o;
+    o.gsz = 1;
+    o.sop_each = o.sop_last = S_SCALE;
+    o.scale = 1.0 / sqrt((double)ctx->n);
+    int id = s;
+    // first pass reads X[s], every pass writes scratch slot 0 (work is indexed by local index)
+    int rc = run_transform(ctx, true, &id, 1, ctx->X, 1, ctx->Tscr, 0, o);
+    if (rc) return rc;
+    *out = ctx->Tscr;
+    return MSM_OK;
+}
+
+int msm_get_psi_interleaved(msm_ctx* ctx, int32_t s, double* out) {
+    if (!ctx || !out || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_get_psi_interleaved: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const double2* d = nullptr;
+    int rc = psi_on_device(ctx, s, &d);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, d, sizeof(double2) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+int msm_get_psi(msm_ctx* ctx, int32_t s, double* re, double* im) {
+    if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_get_psi: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const double2* d = nullptr;
+    int rc = psi_on_device(ctx, s, &d);
+    if (rc) return rc;
+    double* planes = reinterpret_cast<double*>(ctx->P);   // 2*C doubles
+    k_deinterleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, planes, planes + ctx->C, ctx->C);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (re) CU(cudaMemcpyAsync(re, planes, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    if (im) CU(cudaMemcpyAsync(im, planes + ctx->C, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+int msm_get_psik_interleaved(msm_ctx* ctx, int32_t s, double* out) {
+    if (!ctx || !out || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_get_psik_interleaved: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_kspace(ctx, std::vector<int>{s});
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, ctx->X + (size_t)s * ctx->C, sizeof(double2) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+// rho of the listed streams from psi_k (out of place through scratch), into the pair buffers
+static int density_from_psik(msm_ctx* ctx, const int* ids, int ns, bool summed, bool accumulate) {
+    XformOps o;
+    o.sop_last = S_RHO_ONLY;
+    const double n3 = pow((double)ctx->n, (double)ctx->dims);
+    const int sg = ctx->cfg.n_streams_global > 0 ? ctx->cfg.n_streams_global : ctx->S;
+    // un-normalised inverse passes: |psi|^2 = |u|^2 / n^d
+    o.rho_coef = ctx->cfg.density_prefactor / n3 / (summed ? (double)sg : 1.0);
+    o.gsz = summed ? ns : 2;
+    o.p_summed = summed ? 1 : 0;
+    o.rho_accumulate = accumulate ? 1 : 0;
+    return run_transform(ctx, true, ids, ns, ctx->X, 1, ctx->Tscr, 0, o);
+}
+
+int msm_potential_max(msm_ctx* ctx, const int32_t* active, double* out) {
+    if (!ctx || !out) return fail(ctx, MSM_E_ARG, "msm_potential_max: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    std::vector<int> ids = active_list(ctx, active);
+    if (ids.empty()) return MSM_OK;
+    int rc = ensure_kspace(ctx, ids);
+    if (rc) return rc;
+    const bool summed = ctx->cfg.coupling == MSM_COUPLING_SUMMED;
+    CU(cudaMemsetAsync(ctx->maxbits, 0, sizeof(unsigned long long) * (ctx->S + 2), ctx->st));
+    if (!summed) {
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            rc = density_from_psik(ctx, &ids[i], ns, false, false);
+            if (rc) return rc;
+            rc = poisson(ctx, (ns + 1) / 2, true, ctx->maxbits + i);   // maxbits[position in ids]
+            if (rc) return rc;
+        }
+    } else {
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            rc = density_from_psik(ctx, &ids[i], ns, true, i > 0);
+            if (rc) return rc;
+        }
+        rc = allreduce_rho(ctx);
+        if (rc) return rc;
+        rc = poisson(ctx, 1, true, ctx->maxbits);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->h_scal, ctx->maxbits, sizeof(double) * ids.size(), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (size_t i = 0; i < ids.size(); ++i) out[ids[i]] = summed ? ctx->h_scal[0] : ctx->h_scal[i];
+    return MSM_OK;
+}
+
+int msm_get_potential(msm_ctx* ctx, int32_t s, double* phi) {
+    if (!ctx || !phi || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_get_potential: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const bool summed = ctx->cfg.coupling == MSM_COUPLING_SUMMED;
+    int rc;
+    if (!summed) {
+        rc = ensure_kspace(ctx, std::vector<int>{s});
+        if (rc) return rc;
+        int id = s;
+        rc = density_from_psik(ctx, &id, 1, false, false);
+        if (rc) return rc;
+    } else {
+        std::vector<int> ids = active_list(ctx, nullptr);
+        rc = ensure_kspace(ctx, ids);
+        if (rc) return rc;
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            rc = density_from_psik(ctx, &ids[i], ns, true, i > 0);
+            if (rc) return rc;
+        }
+        rc = allreduce_rho(ctx);
+        if (rc) return rc;
+    }
+    rc = poisson(ctx, 1, false, nullptr);
+    if (rc) return rc;
+    double* stage = reinterpret_cast<double*>(ctx->Tscr);
+    k_extract<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->P, stage, ctx->C, 0);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(phi, stage, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+int msm_read_alias(msm_ctx* ctx, double* alias_mass) {
+    if (!ctx || !alias_mass) return fail(ctx, MSM_E_ARG, "msm_read_alias: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaMemcpyAsync(ctx->h_scal, ctx->alias_out, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    for (int s = 0; s < ctx->S; ++s) alias_mass[s] = ctx->h_scal[s];
+    return MSM_OK;
+}
+
+int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const double* kick, double* alias_mass) {
+    if (!ctx || !drift || !kick) return fail(ctx, MSM_E_ARG, "msm_step: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    std::vector<int> ids = active_list(ctx, active);
+    if (ids.empty()) return MSM_OK;
+    int rc = ensure_kspace(ctx, ids);
+    if (rc) return rc;
+    const int n = ctx->n;
+    const bool summed = ctx->cfg.coupling == MSM_COUPLING_SUMMED;
+
+    // per-axis drift tables: exp(-i c k^2) = prod_axes exp(-i c (2 pi k_m)^2); n^(-1/2) per pass = unitary scale
+    CU(cudaEventSynchronize(ctx->dtab_done));
+    const double sc = 1.0 / sqrt((double)n);
+    for (int s : ids) {
+        double2* t = ctx->h_dtab + (size_t)s * n;
+        for (int m = 0; m < n; ++m) {
+            const double th = -drift[s] * (ctx->h_ksq[m] * ctx->four_pi2);
+            t[m] = make_double2(sc * cos(th), sc * sin(th));
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->dtab, ctx->h_dtab, sizeof(double2) * n * ctx->S, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaEventRecord(ctx->dtab_done, ctx->st));
+
+    const int sg = ctx->cfg.n_streams_global > 0 ? ctx->cfg.n_streams_global : ctx->S;
+    auto drift_inverse = [&](const int* cid, int ns, bool accumulate) {
+        XformOps o;   // psi_k * drift -> psi (in place), rho out
+        o.lop_each = L_DRIFT;
+        o.sop_last = S_RHO_KEEP;
+        o.rho_coef = ctx->cfg.density_prefactor / (summed ? (double)sg : 1.0);
+        o.gsz = summed ? ns : 2;
+        o.p_summed = summed ? 1 : 0;
+        o.rho_accumulate = accumulate ? 1 : 0;
+        return run_transform(ctx, true, cid, ns, ctx->X, 1, ctx->X, 1, o);
+    };
+    auto kick_forward = [&](const int* cid, int ns) {
+        XformOps o;   // psi * kick -> psi_k * drift (in place), alias partials out
+        double kk[MAX_CHUNK];
+        for (int i = 0; i < ns; ++i) kk[i] = kick[cid[i]];
+        o.lop_first = L_KICK;
+        o.sop_each = S_DRIFT;
+        o.sop_last = S_DRIFT_ALIAS;
+        o.kick = kk;
+        o.gsz = summed ? ns : 2;
+        o.p_summed = summed ? 1 : 0;
+        return run_transform(ctx, false, cid, ns, ctx->X, 1, ctx->X, 1, o);
+    };
+    if (!summed) {
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            if ((rc = drift_inverse(&ids[i], ns, false))) return rc;
+            if ((rc = poisson(ctx, (ns + 1) / 2, false, nullptr))) return rc;
+            if ((rc = kick_forward(&ids[i], ns))) return rc;
+        }
+    } else {
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            if ((rc = drift_inverse(&ids[i], ns, i > 0))) return rc;
+        }
+        if ((rc = allreduce_rho(ctx))) return rc;
+        if ((rc = poisson(ctx, 1, false, nullptr))) return rc;
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            if ((rc = kick_forward(&ids[i], ns))) return rc;
+        }
+    }
+    {
+        ProfScope ps(ctx, "alias_reduce", 8.0 * ctx->S * ctx->ntiles_last);
+        k_alias_reduce<<<ctx->S, 256, 0, ctx->st>>>(ctx->alias_partial, ctx->alias_out, ctx->ntiles_last, ctx->dv);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (alias_mass) {
+        CU(cudaMemcpyAsync(ctx->h_scal, ctx->alias_out, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        for (int s : ids) alias_mass[s] = ctx->h_scal[s];
+    }
+    return MSM_OK;
+}
+
+int msm_fft(int32_t device, int32_t dims, int32_t size, int32_t inverse, int32_t batch, double* data) {
+    if (!data || batch < 1) return fail(nullptr, MSM_E_ARG, "msm_fft: bad argument");
+    msm_config cfg{};
+    cfg.struct_size = sizeof(msm_config);
+    cfg.dims = dims;
+    cfg.size = size;
+    cfg.n_streams = batch;
+    cfg.device = device;
+    cfg.dx = 1.0;
+    cfg.nranks = 1;
+    msm_ctx* ctx = nullptr;
+    int rc = msm_create(&cfg, &ctx);
+    if (rc) return rc;
+    auto done = [&](int code) {
+        if (code) g_create_error = ctx->err;
+        msm_destroy(ctx);
+        return code;
+    };
+    const size_t cb = sizeof(double2) * (size_t)ctx->C;
+    if (cudaMemcpyAsync(ctx->X, data, cb * batch, cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) return done(MSM_E_CUDA);
+    std::vector<int> ids(batch);
+    for (int i = 0; i < batch; ++i) ids[i] = i;
+    for (int i = 0; i < batch; i += ctx->chunk) {
+        const int ns = std::min(ctx->chunk, batch - i);
+        XformOps o;
+        o.sop_each = o.sop_last = S_SCALE;
+        o.scale = 1.0 / sqrt((double)size);
+        rc = run_transform(ctx, inverse != 0, &ids[i], ns, ctx->X, 1, ctx->X, 1, o);
+        if (rc) return done(rc);
+    }
+    if (cudaMemcpyAsync(data, ctx->X, cb * batch, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return done(MSM_E_CUDA);
+    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) {
+        ctx->err = cudaGetErrorString(cudaGetLastError());
+        return done(MSM_E_CUDA);
+    }
+    return done(MSM_OK);
+}
+
+int msm_spec_grid(int32_t device, int32_t dims, int32_t size, double dx, double* out) {
+    if (!out) return fail(nullptr, MSM_E_ARG, "msm_spec_grid: bad argument");
+    msm_config cfg{};
+    cfg.struct_size = sizeof(msm_config);
+    cfg.dims = dims;
+    cfg.size = size;
+    cfg.n_streams = 1;
+    cfg.device = device;
+    cfg.dx = dx;
+    cfg.nranks = 1;
+    msm_ctx* ctx = nullptr;
+    int rc = msm_create(&cfg, &ctx);
+    if (rc) return rc;
+    double* d = reinterpret_cast<double*>(ctx->Tscr);
+    k_spec_grid<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->ksq, d, size, dims, ctx->four_pi2);
+    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+    if (e != cudaSuccess) g_create_error = cudaGetErrorString(e);
+    msm_destroy(ctx);
+    return e == cudaSuccess ? MSM_OK : MSM_E_CUDA;
+}
+
+// ---- on-device initial conditions -------------------------------------------------------------------------
+static int normalize_on_device(msm_ctx* ctx, double2* psi) {
+    // normalize (utils/grid.rs:11-33): psi *= sqrt(dx^-dims / sum|psi|^2)
+    const int nb = 1024;
+    k_norm2_partial<<<nb, 256, 0, ctx->st>>>(psi, ctx->C, ctx->scratch_small);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    std::vector<double> part(nb);
+    CU(cudaMemcpyAsync(part.data(), ctx->scratch_small, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    double tot = 0.0;
+    for (double v : part) tot += v;
+    const double f = sqrt(pow(ctx->cfg.dx, -(double)ctx->dims) / tot);
+    k_scale_real<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->C, f);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return MSM_OK;
+}
+
+int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double* std) {
+    if (!ctx || !mean || !std || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_cold_gauss: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int n = ctx->n, d = ctx->dims;
+    const double dx = ctx->cfg.dx;
+    // 1-D factors, each normalised with dx^dims as the reference does (ics.rs:91,110,132)
+    std::vector<double> g(3 * n, 1.0);
+    for (int a = 0; a < d; ++a) {
+        double norm = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double x = (double)(2 * i + 1) * dx / 2.0;
+            const double v = exp(-0.5 * pow((x - mean[a]) / std[a], 2.0));
+            g[a * n + i] = v;
+            norm += v * v;
+        }
+        const double f = sqrt(pow(dx, -(double)d) / norm);
+        for (int i = 0; i < n; ++i) g[a * n + i] *= f;
+    }
+    if (3 * n > 4096) return fail(ctx, MSM_E_ARG, "size too large for the IC staging buffer");
+    CU(cudaMemcpyAsync(ctx->scratch_small, g.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    double2* psi = ctx->X + (size_t)s * ctx->C;
+    k_ic_separable<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->scratch_small, n, d, 1.0);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->st));
+    int rc = normalize_on_device(ctx, psi);   // ics.rs:142
+    if (rc) return rc;
+    ctx->in_k[s] = 0;
+    ctx->has_psi[s] = 1;
+    return MSM_OK;
+}
+
+int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t s, double axis_length, double radius, double delta, double slope) {
+    if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_spherical_tophat: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    double2* psi = ctx->X + (size_t)s * ctx->C;
+    const double dx = axis_length / (double)ctx->n;   // ics.rs:203 (axis length, not the comoving box)
+    k_ic_tophat<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->n, ctx->dims, dx, axis_length / 2.0, radius, delta, slope);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    int rc = normalize_on_device(ctx, psi);   // ics.rs:261
+    if (rc) return rc;
+    ctx->in_k[s] = 0;
+    ctx->has_psi[s] = 1;
+    return MSM_OK;
+}
+
+int msm_ic_copy(msm_ctx* ctx, int32_t dst, int32_t src) {
+    if (!ctx || dst < 0 || dst >= ctx->S || src < 0 || src >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_copy: bad argument");
+    if (!ctx->has_psi[src]) return fail(ctx, MSM_E_STATE, "msm_ic_copy: source stream is empty");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (dst != src)
+        CU(cudaMemcpyAsync(ctx->X + (size_t)dst * ctx->C, ctx->X + (size_t)src * ctx->C, sizeof(double2) * (size_t)ctx->C,
+                           cudaMemcpyDeviceToDevice, ctx->st));
+    ctx->in_k[dst] = ctx->in_k[src];
+    ctx->has_psi[dst] = 1;
+    return MSM_OK;
+}
+
+int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t seed, double n_tot) {
+    if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_sample_perturbation: bad argument");
+    if (!ctx->has_psi[s] || ctx->in_k[s]) return fail(ctx, MSM_E_STATE, "msm_sample_perturbation: psi must be freshly set");
+    if (scheme == MSM_SCHEME_NONE) return MSM_OK;
+    if (scheme != MSM_SCHEME_WIGNER && scheme != MSM_SCHEME_HUSIMI)
+        return fail(ctx, MSM_E_ARG, "only the Wigner and Husimi schemes are implemented on device "
+                                    "(the reference's Poisson scheme is unseeded, ics.rs:497)");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const double sqrt_dv = sqrt(pow(ctx->cfg.dx, (double)ctx->dims));
+    const double div = sqrt(n_tot) * (scheme == MSM_SCHEME_WIGNER ? 2.0 : sqrt(2.0));   // ics.rs:581 / :625
+    k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return MSM_OK;
+}
+
+// ---- profiling ---------------------------------------------------------------------------------------------
+int msm_profile_enable(msm_ctx* ctx, int32_t on) {
+    if (!ctx) return MSM_E_ARG;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->st);
+    prof_drain(ctx);
+    ctx->prof = on != 0;
+    if (on) for (auto& r : ctx->prof_rec) r = msm_profile_record{nullptr, 0, 0.0, 0.0};
+    return MSM_OK;
+}
+
+int msm_profile_read(msm_ctx* ctx, msm_profile_record* out, int32_t cap, int32_t* n_out) {
+    if (!ctx || !n_out) return MSM_E_ARG;
+    cudaSetDevice(ctx->cfg.device);
+    prof_drain(ctx);
+    int k = 0;
+    for (size_t i = 0; i < ctx->prof_rec.size(); ++i) {
+        if (ctx->prof_rec[i].launches == 0) continue;
+        if (out && k < cap) {
+            out[k] = ctx->prof_rec[i];
+            out[k].name = ctx->prof_names[i].c_str();
+        }
+        ++k;
+    }
+    *n_out = k;
+    return MSM_OK;
+}
+
+int msm_launch_count(const msm_ctx* ctx, uint64_t* launches) {
+    if (!ctx || !launches) return MSM_E_ARG;
+    *launches = ctx->launches;
+    return MSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// fft_inst.cu -- instantiates the pass kernels for ONE transform length (compile with -DMSM_FFT_N=<N>).
+#include "fft_pass.cuh"
+
+#ifndef MSM_FFT_N
+#error "compile with -DMSM_FFT_N=<power of two>"
+#endif
+
+namespace msm {
+
+#define MSM_CAT2(a, b) a##b
+#define MSM_CAT(a, b) MSM_CAT2(a, b)
+
+namespace {
+constexpr int N = MSM_FFT_N;
+
+template <bool INV, int LOP, int SOP>
+int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
+    using PL = Plan<N>;
+    static bool configured = false;
+    const size_t smem = PL::NS > 1 ? sizeof(double2) * N * PL::T : 0;
+    auto kern = fft_pass_kernel<N, INV, LOP, SOP>;
+    if (!configured) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        configured = true;
+    }
+    dim3 grid(ntiles, groups, 1);
+    kern<<<grid, PL::THREADS, smem, st>>>(p);
+    return (int)cudaPeekAtLastError();
+}
+}  // namespace
+
+// the (direction, load, store) combinations the step actually uses
+int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, const PassParams& p, int ntiles, int groups,
+                                     cudaStream_t st) {
+#define CASE(I, L, S) \
+    if (inv == I && lop == L && sop == S) return launch<I, L, S>(p, ntiles, groups, st);
+    // inverse transforms
+    CASE(true, L_NONE, S_NONE)
+    CASE(true, L_NONE, S_SCALE)
+    CASE(true, L_NONE, S_RHO_ONLY)
+    CASE(true, L_NONE, S_RHO_KEEP)
+    CASE(true, L_NONE, S_MAX)
+    CASE(true, L_DRIFT, S_NONE)
+    CASE(true, L_DRIFT, S_RHO_KEEP)
+    // forward transforms
+    CASE(false, L_NONE, S_NONE)
+    CASE(false, L_NONE, S_SCALE)
+    CASE(false, L_NONE, S_DRIFT)
+    CASE(false, L_NONE, S_DRIFT_ALIAS)
+    CASE(false, L_NONE, S_POISSON)
+    CASE(false, L_KICK, S_DRIFT)
+    CASE(false, L_KICK, S_DRIFT_ALIAS)
+#undef CASE
+    return -1;
+}
+
+}  // namespace msm

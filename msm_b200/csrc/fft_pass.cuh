@@ -1,0 +1,402 @@
+// fft_pass.cuh -- one axis pass of the batched multi-stream complex fp64 FFT, with the point-wise
+// operators of the MSM step fused into its load / store.
+//
+// Replaces (reference, andillio/MSM):
+//   utils/fft.rs:6-98          forward / inverse / *_inplace  (ArrayFire fft3 / ifft3 -> cuFFT inside AF)
+//   simulation_object.rs:504-516,562-574 (static) / :699-708,:771-780 (expanding)   drift  psi_k *= exp(-i c k^2)
+//   simulation_object.rs:535-545 (static) / :726-742 (expanding)                     kick   psi   *= exp(-i kappa phi)
+//   simulation_object.rs:1031-1063   calculate_density    rho = A |psi|^2
+//   simulation_object.rs:1076-1102   phi_k = c rho_k / k^2, k = 0 -> 0
+//   simulation_object.rs:905 / :954  max_all(abs(phi))
+//   simulation_object.rs:1249-1293   check_alias
+//
+// Algorithm: a d-dimensional transform is d passes of length-N 1-D transforms, one per axis.  One CTA owns a
+// tile of T = 8 adjacent lines (adjacent along the fastest array dimension for the strided axes, so that every
+// global access of a quarter warp is one full 128-byte line) and transforms them with a Stockham decimation
+// N = r1*r2*..*rm (radices <= 8, butterflies in registers, E = 8 points per thread), exchanging data between
+// stages through shared memory laid out [position][line]: the 8 lanes of a quarter warp always touch 8
+// consecutive 16-byte words, so every exchange is bank-conflict free without swizzling.  The CTA then repeats the
+// tile for the next stream of its group (two streams share one complex "pair buffer" for the real fields
+// rho / phi: rho_a + i rho_b -- the Poisson operator is real and linear, so one complex solve serves two streams).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msm {
+
+constexpr int MAX_CHUNK = 16;   // streams per launch group
+
+enum LoadOp { L_NONE = 0, L_DRIFT = 1, L_KICK = 2 };
+enum StoreOp {
+    S_NONE = 0,         // plain store
+    S_SCALE = 1,        // * scale
+    S_DRIFT = 2,        // * dtab[stream][k]                     (forward passes of the kick->drift transform)
+    S_DRIFT_ALIAS = 3,  // S_DRIFT + masked |psi_k|^2 partial sum  (last forward pass)
+    S_RHO_KEEP = 4,     // store psi and rho = rho_coef |psi|^2    (last inverse pass of the drift transform)
+    S_RHO_ONLY = 5,     // rho only, psi is not written            (potential at time t: only max|phi| is needed)
+    S_POISSON = 6,      // * poisson_coef / k^2, DC -> 0           (last forward pass of the Poisson solve)
+    S_MAX = 7           // no store, max|re| and max|im|           (last inverse pass of the dt Poisson solve)
+};
+
+struct PassParams {
+    const double2* src;
+    double2* dst;
+    long long src_sstride, dst_sstride;   // elements between stream slots
+    int src_by_sid, dst_by_sid;           // slot = stream id (resident array) or local index (scratch)
+    int ns, gsz;                          // streams in this launch, streams per CTA group
+    int sid[MAX_CHUNK];
+    // tile geometry:  offset(tile, l, e) = (tile / tiles_inner) * outer_stride + (tile % tiles_inner) * inner_stride
+    //                                      + l * lstride + e * astride
+    int axis;                             // 0 = contiguous (x), 1 = stride n (y), 2 = stride n^2 (z)
+    int n;
+    int tiles_inner;
+    long long outer_stride, inner_stride, lstride, astride;
+    int lvalid;                           // valid lines per tile (1-D grids have a single line)
+    // operators
+    const double2* twiddle;               // N entries  exp(-2 pi i j / N)
+    const double2* dtab;                  // [n_streams][N]  per-axis drift factors (scale folded in), by stream id
+    double kick[MAX_CHUNK];               // kappa per local index
+    double2* pbuf;                        // pair buffers (rho / phi)
+    long long p_gstride;
+    int p_summed;                         // 1: all streams accumulate into buffer 0 component x
+    int rho_accumulate;                   // summed mode: add to what is already in the buffer
+    const double* ksq;                    // (k_m)^2 = (m_signed / (n dx))^2, n entries  (utils/fft.rs:100-120)
+    double four_pi2, alias_k2_thresh, poisson_coef, rho_coef, scale;
+    double* alias_partial;                // [n_streams][ntiles] by stream id
+    int ntiles;
+    unsigned long long* maxbits;          // [2 * buffers]: bit patterns of non-negative doubles
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// decomposition plans
+// ----------------------------------------------------------------------------------------------------------
+template <int N> struct Plan;
+#define MSM_PLAN(N_, E_, T_, MINB_, NS_, R0, R1, R2, R3)                                   \
+    template <> struct Plan<N_> {                                                          \
+        static constexpr int E = E_, T = T_, MINB = MINB_, NS = NS_;                       \
+        static constexpr int NT = N_ / E_;                                                 \
+        static constexpr int THREADS = NT * T_;                                            \
+        static constexpr int R[4] = {R0, R1, R2, R3};                                      \
+    };
+//        N    E  T  minB stages radices
+MSM_PLAN(2,    2, 2,  1, 1, 2, 1, 1, 1)
+MSM_PLAN(4,    4, 4,  1, 1, 4, 1, 1, 1)
+MSM_PLAN(8,    8, 8,  1, 1, 8, 1, 1, 1)
+MSM_PLAN(16,   8, 8,  1, 2, 2, 8, 1, 1)
+MSM_PLAN(32,   8, 8,  1, 2, 4, 8, 1, 1)
+MSM_PLAN(64,   8, 8,  1, 2, 8, 8, 1, 1)
+MSM_PLAN(128,  8, 8,  1, 3, 2, 8, 8, 1)
+MSM_PLAN(256,  8, 8,  2, 3, 4, 8, 8, 1)
+MSM_PLAN(512,  8, 8,  2, 3, 8, 8, 8, 1)
+MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
+#undef MSM_PLAN
+
+template <int N> constexpr int plan_L(int q) {   // product of radices of stages < q
+    int l = 1;
+    for (int i = 0; i < q; ++i) l *= Plan<N>::R[i];
+    return l;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// complex helpers
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> __device__ __forceinline__ double2 rot90(double2 a) {
+    return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+template <int R, bool INV> struct Dft;
+template <bool INV> struct Dft<1, INV> {
+    static __device__ __forceinline__ void run(double2*) {}
+};
+template <bool INV> struct Dft<2, INV> {
+    static __device__ __forceinline__ void run(double2* v) {
+        double2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <bool INV> struct Dft<4, INV> {
+    static __device__ __forceinline__ void run(double2* v) {
+        double2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        double2 t2 = cadd(v[1], v[3]), t3 = rot90<INV>(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = cadd(t1, t3);
+        v[3] = csub(t1, t3);
+    }
+};
+template <bool INV> struct Dft<8, INV> {
+    static __device__ __forceinline__ void run(double2* v) {
+        constexpr double h = 0.70710678118654752440;
+        // even / odd radix-4
+        double2 e[4] = {v[0], v[2], v[4], v[6]};
+        double2 o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4, INV>::run(e);
+        Dft<4, INV>::run(o);
+        // W8^1 = (1 -+ i)/sqrt2, W8^2 = -+ i, W8^3 = (-1 -+ i)/sqrt2   (upper sign forward)
+        double2 o1, o3;
+        if (INV) {
+            o1 = make_double2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y));
+            o3 = make_double2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y));
+        } else {
+            o1 = make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+            o3 = make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+        }
+        double2 o2 = rot90<INV>(o[2]);
+        v[0] = cadd(e[0], o[0]);
+        v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], o1);
+        v[5] = csub(e[1], o1);
+        v[2] = cadd(e[2], o2);
+        v[6] = csub(e[2], o2);
+        v[3] = cadd(e[3], o3);
+        v[7] = csub(e[3], o3);
+    }
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// block reductions (deterministic order)
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// the pass kernel
+// ----------------------------------------------------------------------------------------------------------
+// Stage q (0-based) transforms digit n_q into k_q.  With L = r_0..r_{q-1}, M = N / (L r_q):
+//   butterfly b in [0, N / r_q):  kappa = b / M, nu = b % M
+//   inputs   position kappa * (M r_q) + n * M + nu          (n = 0..r_q-1)
+//   outputs  position (kappa + L k) * M + nu                 (k = 0..r_q-1), twiddle W_N^(k L nu)
+// positions of stage 0 inputs are element indices of the line, positions of the last stage outputs are the
+// output indices (natural order).
+template <int N, bool INV, int Q>
+__device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm, int t, int l,
+                                           const double2* __restrict__ tw) {
+    using PL = Plan<N>;
+    constexpr int E = PL::E, T = PL::T, NT = PL::NT;
+    constexpr int R = PL::R[Q];
+    constexpr int L = plan_L<N>(Q);
+    constexpr int M = N / (L * R);
+    constexpr int NB = E / R;   // butterflies per thread in this stage
+#pragma unroll
+    for (int c = 0; c < NB; ++c) Dft<R, INV>::run(&v[c * R]);
+    if constexpr (Q + 1 < PL::NS) {
+        // twiddle + scatter to the exchange buffer
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            const int b = t + NT * c;
+            const int kappa = b / M, nu = b % M;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                double2 x = v[c * R + k];
+                if (k > 0) {
+                    double2 w = __ldg(&tw[k * L * nu]);
+                    if (INV) w.y = -w.y;
+                    x = cmul(x, w);
+                }
+                sm[((kappa + L * k) * M + nu) * T + l] = x;
+            }
+        }
+        __syncthreads();
+        constexpr int R2 = PL::R[Q + 1];
+        constexpr int L2 = L * R;
+        constexpr int M2 = N / (L2 * R2);
+        constexpr int NB2 = E / R2;
+#pragma unroll
+        for (int c = 0; c < NB2; ++c) {
+            const int b = t + NT * c;
+            const int kappa = b / M2, nu = b % M2;
+#pragma unroll
+            for (int n = 0; n < R2; ++n) v[c * R2 + n] = sm[(kappa * (M2 * R2) + n * M2 + nu) * T + l];
+        }
+        __syncthreads();
+        run_stages<N, INV, Q + 1>(v, sm, t, l, tw);
+    }
+}
+
+template <int N, bool INV, int LOP, int SOP>
+__global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kernel(const PassParams p) {
+    using PL = Plan<N>;
+    constexpr int E = PL::E, T = PL::T, NT = PL::NT;
+    constexpr int R0 = PL::R[0];
+    constexpr int M0 = N / R0;
+    constexpr int NB0 = E / R0;
+    constexpr int RL = PL::R[PL::NS - 1];
+    constexpr int LL = plan_L<N>(PL::NS - 1);
+    constexpr int NBL = E / RL;
+
+    extern __shared__ double2 sm[];
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x;
+    const int l = tid % T, t = tid / T;
+    const int tile = blockIdx.x;
+    const bool lv = l < p.lvalid;
+    const long long base = (long long)(tile / p.tiles_inner) * p.outer_stride +
+                           (long long)(tile % p.tiles_inner) * p.inner_stride + (long long)l * p.lstride;
+
+    // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
+    double kline = 0.0;   // partial k^2 sum in the reference's order (see k2_of)
+    int c0 = 0, c1 = 0, c2 = 0;
+    if constexpr (SOP == S_DRIFT_ALIAS || SOP == S_POISSON) {
+        const int n = p.n;
+        if (p.axis == 0) {
+            const int line = tile * T + l;
+            c1 = line % n;
+            c2 = line / n;
+        } else if (p.axis == 1) {
+            c2 = tile / p.tiles_inner;
+            c0 = (tile % p.tiles_inner) * T + l;
+        } else {
+            const int line = tile * T + l;
+            c1 = line / n;
+            c0 = line % n;
+        }
+        if (!lv) c0 = c1 = c2 = 0;
+        // spec_grid sums ((k0^2 + k1^2) + k2^2) * (2 pi)^2 with dim 0 the fastest axis (utils/fft.rs:141-160)
+        if (p.axis == 2) kline = p.ksq[c0] + p.ksq[c1];
+    }
+    auto k2_of = [&](int e) -> double {
+        double s;
+        if (p.axis == 0) s = (p.ksq[e] + p.ksq[c1]) + p.ksq[c2];
+        else if (p.axis == 1) s = (p.ksq[c0] + p.ksq[e]) + p.ksq[c2];
+        else s = kline + p.ksq[e];
+        return s * p.four_pi2;
+    };
+
+    const int g = blockIdx.y;
+    for (int q = 0; q < p.gsz; ++q) {
+        const int li = g * p.gsz + q;
+        if (li >= p.ns) break;
+        const int s = p.sid[li];
+        const double2* __restrict__ src = p.src + (long long)(p.src_by_sid ? s : li) * p.src_sstride;
+        double2* __restrict__ dst = p.dst + (long long)(p.dst_by_sid ? s : li) * p.dst_sstride;
+        double2* __restrict__ pb = p.pbuf + (p.p_summed ? 0 : (long long)g * p.p_gstride);
+        const int comp = p.p_summed ? 0 : q;
+
+        double2 v[E];
+        // ---- load (stage-0 input order) ----
+#pragma unroll
+        for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+            for (int n = 0; n < R0; ++n) {
+                const int e = n * M0 + t + NT * c;
+                const long long off = base + (long long)e * p.astride;
+                double2 x = make_double2(0.0, 0.0);
+                if (lv) x = src[off];
+                if constexpr (LOP == L_DRIFT) {
+                    const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
+                    x = cmul(x, w);
+                }
+                if constexpr (LOP == L_KICK) {
+                    // psi *= exp(-i kappa phi)    (simulation_object.rs:535-545)
+                    double ph = 0.0;
+                    if (lv) {
+                        const double* pd = reinterpret_cast<const double*>(pb + off);
+                        ph = pd[comp];
+                    }
+                    double sn, cs;
+                    sincos(-p.kick[li] * ph, &sn, &cs);
+                    x = cmul(x, make_double2(cs, sn));
+                }
+                v[c * R0 + n] = x;
+            }
+        }
+
+        run_stages<N, INV, 0>(v, sm, t, l, p.twiddle);
+
+        // ---- store (last-stage output order) ----
+        double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+            for (int k = 0; k < RL; ++k) {
+                const int e = t + NT * c + LL * k;
+                const long long off = base + (long long)e * p.astride;
+                double2 x = v[c * RL + k];
+                if constexpr (SOP == S_SCALE) {
+                    x.x *= p.scale;
+                    x.y *= p.scale;
+                }
+                if constexpr (SOP == S_DRIFT || SOP == S_DRIFT_ALIAS) {
+                    const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
+                    x = cmul(x, w);
+                }
+                if constexpr (SOP == S_DRIFT_ALIAS) {
+                    // check_alias: sum |psi_k|^2 where k^2 > k2_cutoff * k2_max  (simulation_object.rs:1259-1280)
+                    if (lv && k2_of(e) > p.alias_k2_thresh) acc += x.x * x.x + x.y * x.y;
+                }
+                if constexpr (SOP == S_POISSON) {
+                    // phi_k = c rho_k / k^2, 0/0 at k = 0 replaced by 0  (simulation_object.rs:1076-1102)
+                    const double k2 = k2_of(e);
+                    const double m = (k2 == 0.0) ? 0.0 : p.poisson_coef / k2;
+                    x.x *= m;
+                    x.y *= m;
+                }
+                if constexpr (SOP == S_MAX) {
+                    acc = fmax(acc, fabs(x.x));
+                    acc2 = fmax(acc2, fabs(x.y));
+                }
+                if constexpr (SOP == S_RHO_KEEP || SOP == S_RHO_ONLY) {
+                    // rho = A real(psi conj(psi))   (simulation_object.rs:1051-1062)
+                    const double rho = p.rho_coef * (x.x * x.x + x.y * x.y);
+                    if (lv) {
+                        double* pd = reinterpret_cast<double*>(pb + off);
+                        if (p.p_summed) {
+                            pd[0] = (p.rho_accumulate || q > 0) ? pd[0] + rho : rho;
+                            if (!(p.rho_accumulate || q > 0)) pd[1] = 0.0;
+                        } else {
+                            pd[comp] = rho;
+                            if (q == 0 && li + 1 >= p.ns) pd[1] = 0.0;   // odd stream count: empty partner
+                        }
+                    }
+                }
+                if constexpr (SOP != S_RHO_ONLY && SOP != S_MAX) {
+                    if (lv) dst[off] = x;
+                }
+            }
+        }
+
+        if constexpr (SOP == S_DRIFT_ALIAS) {
+            acc = warp_sum(acc);
+            if ((tid & 31) == 0) red[tid >> 5] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < (PL::THREADS + 31) / 32; ++w) tot += red[w];
+                p.alias_partial[(long long)s * p.ntiles + tile] = tot;
+            }
+            __syncthreads();
+        }
+        if constexpr (SOP == S_MAX) {
+            acc = warp_max(acc);
+            acc2 = warp_max(acc2);
+            if ((tid & 31) == 0) {
+                atomicMax(&p.maxbits[2 * li], (unsigned long long)__double_as_longlong(acc));
+                atomicMax(&p.maxbits[2 * li + 1], (unsigned long long)__double_as_longlong(acc2));
+            }
+        }
+    }
+}
+
+// host-side launcher, one translation unit per N (fft_inst.cu compiled with -DMSM_FFT_N=<N>)
+typedef int (*pass_launcher_t)(bool inv, int lop, int sop, const PassParams& p, int ntiles, int groups,
+                               cudaStream_t st);
+pass_launcher_t get_pass_launcher(int n);
+const char* pass_kernel_name(int n, bool inv, int lop, int sop);
+
+}  // namespace msm

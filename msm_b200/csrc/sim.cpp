@@ -1,0 +1,481 @@
+// sim.cpp -- host-logic level of the C ABI (msm_sim_*): a C++ mirror of the reference's `SimulationObject`
+// (simulator/src/simulation_object.rs:145-184) batched over streams.  Everything here is host scalars; the grid
+// work is delegated to the grid-level calls msm_potential_max / msm_step (core.cu).
+//
+// Reference rows: a2 SimulationParameters::new (:223-315), a7 get_timestep static
+// (:878-934), a8 get_timestep expanding (:939-990), a13 update bookkeeping (:590,:620-635 / :757-759,:828-844),
+// a14 dump (utils/io.rs:34-88), a15 not_finished (:1226-1228), a16 ScaleFactorSolver (expanding.rs:12-118),
+// rk4 (utils/mod.rs:14-43), calculate_dt_from_dtau (:1344-1388), get_tau (:1408-1453),
+// get_supercomoving_boxsize (common/src/parameters.rs:205-220).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/msm_b200.h"
+
+namespace {
+
+// common/src/constants.rs:2-9
+const double POIS_CONST = 4.0 * M_PI * 4.49e-12;
+const double LITTLE_H_TO_BIG_H = 1.022e-4;
+const double DEFAULT_MAX_DLOGA = 1e-3;   // expanding.rs:27
+
+struct Cosmo {
+    double om = 0, orad = 0, h = 0, z0 = 0, max_dloga = 0;
+    bool has_max_dloga = false;
+};
+
+// utils/mod.rs:14-43
+double rk4(const std::function<double(double, double)>& f, double tn, double yn, double h) {
+    const double k1 = f(tn, yn);
+    const double k2 = f(tn + h / 2.0, yn + h * k1 / 2.0);
+    const double k3 = f(tn + h / 2.0, yn + h * k2 / 2.0);
+    const double k4 = f(tn + h, yn + h * k3);
+    return yn + h * (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0;
+}
+
+// expanding.rs:12-118.  The reference wraps crate `cosmology` 0.2.0 (not vendored).  Restated as flat FLRW,
+// omega_de0 = 1 - om - or (expanding.rs:29-38), H0 = h * 1.022e-4 / Myr, a(0) = 1/(1+z0),
+// da/dt = a H0 sqrt(om a^-3 + or a^-4 + ode), RK4 sub-steps bounded by max_dloga * a / (da/dt); negative dt
+// steps backwards with the same rule.  Identical to oracle/msm_oracle.py::ScaleFactorSolver.
+struct ScaleFactorSolver {
+    double om = 0, orad = 0, ode = 0, h0 = 0, max_dloga = DEFAULT_MAX_DLOGA, a = 1, t = 0;
+    ScaleFactorSolver() {}
+    explicit ScaleFactorSolver(const Cosmo& c) {
+        om = c.om;
+        orad = c.orad;
+        ode = 1.0 - om - orad;
+        h0 = c.h * LITTLE_H_TO_BIG_H;
+        max_dloga = c.has_max_dloga ? c.max_dloga : DEFAULT_MAX_DLOGA;
+        a = 1.0 / (1.0 + c.z0);
+        t = 0.0;
+    }
+    double dadt(double x) const { return x * h0 * sqrt(om / (x * x * x) + orad / (x * x * x * x) + ode); }
+    double step(double dt) {
+        double remaining = dt;
+        while (remaining != 0.0) {
+            const double lim = max_dloga * a / dadt(a);
+            const double h = fabs(remaining) <= lim ? remaining : copysign(lim, remaining);
+            const double k1 = dadt(a);
+            const double k2 = dadt(a + 0.5 * h * k1);
+            const double k3 = dadt(a + 0.5 * h * k2);
+            const double k4 = dadt(a + h * k3);
+            a = a + h * (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0;
+            t += h;
+            remaining = (h == remaining) ? 0.0 : remaining - h;
+        }
+        return a;
+    }
+    double get_a() const { return a; }
+    double get_dadt() const { return dadt(a); }
+    double get_time() const { return t; }
+};
+
+// simulation_object.rs:1408-1453
+double get_tau(double target_time, const Cosmo& c) {
+    ScaleFactorSolver solver(c);
+    const double pref = sqrt(1.5 * c.om * pow(LITTLE_H_TO_BIG_H * c.h, 2));
+    auto dtau_dt = [&](double t, double) {
+        const double a_at_t = solver.step(t - solver.get_time());
+        return pref / (a_at_t * a_at_t);
+    };
+    double tau = 0.0, time = 0.0;
+    while (time < target_time) {
+        double dt = target_time / 1000.0;
+        if (c.has_max_dloga) dt = fmin(target_time / 1000.0, solver.get_a() / solver.get_dadt() * c.max_dloga);
+        dt = fmin(dt, target_time - time);
+        tau = rk4(dtau_dt, time, tau, dt);
+        time += dt;
+    }
+    return tau;
+}
+
+// common/src/parameters.rs:205-220
+double supercomoving_boxsize(double hbar_, const Cosmo& c, double axis_length) {
+    const double a0 = 1.0 / (1.0 + c.z0);
+    const double comoving = axis_length / a0;
+    return sqrt(sqrt(1.5 * c.om * pow(LITTLE_H_TO_BIG_H * c.h, 2)) / hbar_) * comoving;
+}
+
+struct Stream {
+    double time = 0, tau = 0, dt = 0, potential_max = 0, alias_mass = 0;
+    uint64_t n_steps = 0;
+    uint32_t current_dumps = 0;
+    int dumped = 0, aliased = 0;
+    ScaleFactorSolver solver;
+};
+
+}  // namespace
+
+struct msm_sim {
+    msm_sim_params p{};
+    msm_derived d{};
+    Cosmo cosmo;
+    msm_ctx* ctx = nullptr;
+    std::vector<Stream> st;
+    std::vector<std::thread> io;
+    std::string err;
+};
+
+namespace {
+std::string g_sim_error;
+int sfail(msm_sim* s, int code, const std::string& m) {
+    if (s) s->err = m; else g_sim_error = m;
+    return code;
+}
+
+bool not_finished(const msm_sim* s, const Stream& st) { return st.time < s->p.final_sim_time; }   // :1226-1228
+
+// simulation_object.rs:878-934 / :939-990
+void get_timestep(const msm_sim* sim, const Stream& st, double potential_max, bool* dump, double* dt_out) {
+    const msm_sim_params& p = sim->p;
+    const double time_to_next_dump =
+        ((double)(st.current_dumps + 1) * p.final_sim_time / (double)p.num_data_dumps) - st.time;   // :916-919
+    if (!p.expanding) {
+        const double kinetic_dt = p.cfl * 2.0 * p.axis_length / sqrt(sim->d.k2_max) / p.hbar_;        // :881-884
+        const double potential_dt = p.cfl * (2.0 * M_PI) * p.hbar_ / (2.0 * potential_max);           // :906-909
+        const double dt = fmin(fmin(kinetic_dt, potential_dt), time_to_next_dump);                    // :922
+        *dump = (dt == time_to_next_dump);                                                            // :927
+        *dt_out = dt;
+        return;
+    }
+    const double kinetic_dtau = p.cfl * 2.0 * sim->d.comoving_boxsize / sqrt(sim->d.k2_max);          // :942-944
+    const double potential_dtau = p.cfl * (2.0 * M_PI) / ((2.0 * st.solver.get_a()) * potential_max); // :957-959
+    const double tau_to_next_dump = get_tau(st.time + time_to_next_dump, sim->cosmo) - st.tau;        // :970-975
+    const double dtau = fmin(fmin(kinetic_dtau, potential_dtau), tau_to_next_dump);                   // :978
+    *dump = (dtau == tau_to_next_dump);                                                               // :983
+    *dt_out = dtau;
+}
+
+// simulation_object.rs:1344-1388
+double calculate_dt_from_dtau(const msm_sim* sim, const Stream& st, double dtau) {
+    ScaleFactorSolver solver = st.solver;   // clone
+    const double pref = sqrt(1.5 * sim->cosmo.om * pow(LITTLE_H_TO_BIG_H * sim->cosmo.h, 2));
+    auto dt_dtau = [&](double, double t) {
+        const double a_at_t = solver.step(t - solver.get_time());
+        return 1.0 / (pref / (a_at_t * a_at_t));
+    };
+    return rk4(dt_dtau, st.tau, st.time, dtau) - st.time;
+}
+
+// NPY v1.0 writer for one f64 plane, shape (n, n|1, n|1, 1)   (utils/io.rs:63-66,90-97)
+bool write_npy(const std::string& path, const double* data, int dims, int n) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    char dict[160];
+    const int s1 = dims >= 2 ? n : 1, s2 = dims >= 3 ? n : 1;
+    int len = snprintf(dict, sizeof dict, "{'descr': '<f8', 'fortran_order': False, 'shape': (%d, %d, %d, 1), }", n, s1, s2);
+    const int unpadded = 10 + len + 1;
+    const int pad = (64 - unpadded % 64) % 64;
+    const uint16_t hlen = (uint16_t)(len + pad + 1);
+    const unsigned char magic[8] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+    bool ok = fwrite(magic, 1, 8, f) == 8;
+    ok = ok && fwrite(&hlen, 2, 1, f) == 1;
+    ok = ok && fwrite(dict, 1, len, f) == (size_t)len;
+    for (int i = 0; i < pad && ok; ++i) ok = fputc(' ', f) != EOF;
+    ok = ok && fputc('\n', f) != EOF;
+    size_t count = 1;
+    for (int d = 0; d < dims; ++d) count *= (size_t)n;
+    ok = ok && fwrite(data, sizeof(double), count, f) == count;
+    ok = (fclose(f) == 0) && ok;
+    return ok;
+}
+
+void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i < path.size(); ++i) {
+        cur.push_back(path[i]);
+        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0777);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* msm_sim_last_error(const msm_sim* sim) { return sim ? sim->err.c_str() : g_sim_error.c_str(); }
+
+double msm_get_tau(double target_time, double om, double orad, double h, double z0, double max_dloga, int32_t has) {
+    Cosmo c;
+    c.om = om; c.orad = orad; c.h = h; c.z0 = z0; c.max_dloga = max_dloga; c.has_max_dloga = has != 0;
+    return get_tau(target_time, c);
+}
+
+double msm_supercomoving_boxsize(double hbar_, double om, double h, double z0, double axis_length) {
+    Cosmo c;
+    c.om = om; c.h = h; c.z0 = z0;
+    return supercomoving_boxsize(hbar_, c, axis_length);
+}
+
+double msm_scale_factor_after(double t, double om, double orad, double h, double z0, double max_dloga) {
+    Cosmo c;
+    c.om = om; c.orad = orad; c.h = h; c.z0 = z0; c.max_dloga = max_dloga; c.has_max_dloga = true;
+    ScaleFactorSolver s(c);
+    return s.step(t);
+}
+
+int msm_sim_create(const msm_sim_params* p, msm_sim** out) {
+    if (!p || !out) return sfail(nullptr, MSM_E_ARG, "null argument");
+    *out = nullptr;
+    if (p->struct_size != (int32_t)sizeof(msm_sim_params)) return sfail(nullptr, MSM_E_ARG, "msm_sim_params.struct_size mismatch");
+    if (p->num_data_dumps == 0) return sfail(nullptr, MSM_E_ARG, "num_data_dumps must be > 0");
+    if (p->size < 2 || (p->size % 2)) return sfail(nullptr, MSM_E_ARG, "size must be even (utils/fft.rs:105)");
+    msm_sim* s = new msm_sim();
+    s->p = *p;
+    s->cosmo.om = p->omega_matter_now;
+    s->cosmo.orad = p->omega_radiation_now;
+    s->cosmo.h = p->h;
+    s->cosmo.z0 = p->z0;
+    s->cosmo.max_dloga = p->max_dloga;
+    s->cosmo.has_max_dloga = p->has_max_dloga != 0;
+
+    // SimulationParameters::new (simulation_object.rs:243-274)
+    msm_derived& d = s->d;
+    d.tau0 = 0.0;
+    d.final_sim_tau = 0.0;
+    d.comoving_boxsize = 0.0;
+    if (p->expanding) {
+        if (p->omega_matter_now + p->omega_radiation_now > 1.0 || p->z0 < 0.0 || p->omega_matter_now < 0.0 ||
+            p->omega_radiation_now < 0.0) {   // expanding.rs:62-80
+            delete s;
+            return sfail(nullptr, MSM_E_ARG, "only flat cosmologies with z0 >= 0 are supported");
+        }
+        d.tau0 = get_tau(p->time, s->cosmo);                                     // :246
+        d.final_sim_tau = get_tau(p->final_sim_time, s->cosmo);                  // :248-249
+        d.comoving_boxsize = supercomoving_boxsize(p->hbar_, s->cosmo, p->axis_length);   // :251-256
+        d.dx = d.comoving_boxsize / (double)p->size;                             // :262
+    } else {
+        d.dx = p->axis_length / (double)p->size;                                 // :260
+    }
+    d.dk = d.dx;                                                                 // :263
+    d.n_tot = p->total_mass / p->particle_mass;                                  // :264
+    {   // k2_max = max(spec_grid): every axis at its Nyquist index, summed in spec_grid's order (fft.rs:141-160)
+        const double kn = (double)(-(p->size / 2)) / ((double)p->size * d.dx);
+        const double m = kn * kn;
+        double sum = m;
+        if (p->dims >= 2) sum = sum + m;
+        if (p->dims >= 3) sum = sum + m;
+        d.k2_max = sum * ((2.0 * M_PI) * (2.0 * M_PI));
+    }
+    if (p->expanding)   // calculate_density :1033-1048
+        d.density_prefactor = p->total_mass * POIS_CONST *
+                              pow(2.0 / (3.0 * pow(p->h * LITTLE_H_TO_BIG_H, 2) * p->omega_matter_now), 1.0 / 4.0) /
+                              pow(p->hbar_, (double)p->dims / 2.0);
+    else
+        d.density_prefactor = p->total_mass;                                     // :1056
+    d.poisson_coeff = p->expanding ? -1.0 : -POIS_CONST;                         // :1079-1086
+
+    msm_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof(msm_config);
+    cfg.dims = p->dims;
+    cfg.size = p->size;
+    cfg.n_streams = p->n_streams;
+    cfg.coupling = p->coupling;
+    cfg.device = p->device;
+    cfg.chunk_streams = p->chunk_streams;
+    cfg.rank = p->rank;
+    cfg.nranks = p->nranks > 0 ? p->nranks : 1;
+    cfg.n_streams_global = p->n_streams_global;
+    cfg.dx = d.dx;
+    cfg.density_prefactor = d.density_prefactor;
+    cfg.poisson_coeff = d.poisson_coeff;
+    cfg.k2_cutoff = p->k2_cutoff;
+    cfg.nccl_unique_id = p->nccl_unique_id;
+    int rc = msm_create(&cfg, &s->ctx);
+    if (rc) {
+        g_sim_error = msm_last_error(nullptr);
+        delete s;
+        return rc;
+    }
+    s->st.resize(p->n_streams);
+    for (auto& st : s->st) {
+        st.time = p->time;
+        st.tau = d.tau0;
+        if (p->expanding) st.solver = ScaleFactorSolver(s->cosmo);               // new_from_params :437-438
+    }
+    *out = s;
+    return MSM_OK;
+}
+
+int msm_sim_wait_io(msm_sim* sim) {
+    if (!sim) return MSM_E_ARG;
+    for (auto& t : sim->io)
+        if (t.joinable()) t.join();
+    sim->io.clear();
+    return MSM_OK;
+}
+
+void msm_sim_destroy(msm_sim* sim) {
+    if (!sim) return;
+    msm_sim_wait_io(sim);
+    msm_destroy(sim->ctx);
+    delete sim;
+}
+
+msm_ctx* msm_sim_ctx(msm_sim* sim) { return sim ? sim->ctx : nullptr; }
+
+int msm_sim_derived(const msm_sim* sim, msm_derived* out) {
+    if (!sim || !out) return MSM_E_ARG;
+    *out = sim->d;
+    return MSM_OK;
+}
+
+int msm_sim_set_psi(msm_sim* sim, int32_t stream, const double* psi) {
+    if (!sim) return MSM_E_ARG;
+    int rc = msm_set_psi(sim->ctx, stream, psi);
+    if (rc) sim->err = msm_last_error(sim->ctx);
+    return rc;
+}
+
+int msm_sim_not_finished(const msm_sim* sim) {
+    if (!sim) return 0;
+    for (const auto& st : sim->st)
+        if (not_finished(sim, st)) return 1;
+    return 0;
+}
+
+int msm_sim_update(msm_sim* sim) {
+    if (!sim) return MSM_E_ARG;
+    const msm_sim_params& p = sim->p;
+    const int S = p.n_streams;
+    const bool summed = p.coupling == MSM_COUPLING_SUMMED;
+    std::vector<int32_t> active(S, 0);
+    int nact = 0;
+    for (int s = 0; s < S; ++s) {
+        sim->st[s].dumped = 0;
+        if (not_finished(sim, sim->st[s])) {
+            active[s] = 1;
+            ++nact;
+        }
+    }
+    if (nact == 0) return MSM_OK;
+
+    // calculate_potential at t + max_all(abs(phi))  (:497 -> :905)
+    std::vector<double> pmax(S, 0.0), drift(S, 0.0), kick(S, 0.0), alias(S, 0.0), dts(S, 0.0);
+    std::vector<char> dump(S, 0);
+    int rc = msm_potential_max(sim->ctx, active.data(), pmax.data());
+    if (rc) {
+        sim->err = msm_last_error(sim->ctx);
+        return rc;
+    }
+    for (int s = 0; s < S; ++s) {
+        if (!active[s]) continue;
+        Stream& st = sim->st[s];
+        bool dmp = false;
+        double dt = 0.0;
+        get_timestep(sim, st, pmax[s], &dmp, &dt);                               // :500 / :695
+        if (summed && s > 0) {   // shared potential => identical scalars; keep the streams in lock step
+            int h = 0;
+            while (!active[h]) ++h;
+            dmp = dump[h];
+            dt = dts[h];
+        }
+        dump[s] = dmp;
+        dts[s] = dt;
+        st.dt = dt;
+        st.potential_max = pmax[s];
+        if (!p.expanding) {
+            drift[s] = dt / 4.0 * p.hbar_;                                       // :508
+            kick[s] = dt / p.hbar_;                                              // :537
+        } else {
+            drift[s] = dt / 4.0;                                                 // :701
+            double ksum = 0.0;
+            for (int j = 0; j < 2; ++j) {                                        // :726-760
+                const double a = st.solver.get_a();                              // :728
+                ksum += dt / 2.0 * a;                                            // :733 (both half kicks use the same phi)
+                const double dt_half = calculate_dt_from_dtau(sim, st, dt / 2.0);   // :751-752
+                st.solver.step(dt_half);                                         // :755-756
+                st.time = st.time + dt_half;                                     // :757
+                st.tau = st.tau + dt / 2.0;                                      // :759
+            }
+            kick[s] = ksum;
+        }
+    }
+    rc = msm_step(sim->ctx, active.data(), drift.data(), kick.data(), alias.data());
+    if (rc) {
+        sim->err = msm_last_error(sim->ctx);
+        return rc;
+    }
+    int result = MSM_OK;
+    for (int s = 0; s < S; ++s) {
+        if (!active[s]) continue;
+        Stream& st = sim->st[s];
+        if (!p.expanding) st.time = st.time + dts[s];                            // :590
+        st.alias_mass = alias[s];
+        st.aliased = alias[s] > p.alias_threshold ? 1 : 0;                       // :1288
+        if (st.aliased) {
+            result = MSM_E_ALIASING;                                             // the reference panics here (:607-617)
+            char buf[160];
+            snprintf(buf, sizeof buf, "simulation aliased: stream %d threshold %g k2_cutoff %g p_mass %g", s,
+                     p.alias_threshold, p.k2_cutoff, alias[s]);
+            sim->err = buf;
+        }
+        if (dump[s]) {                                                           // :620-631 / :828-844
+            st.current_dumps += 1;
+            st.dumped = 1;
+            st.time = (double)st.current_dumps * p.final_sim_time / (double)p.num_data_dumps;
+            if (p.expanding) st.tau = get_tau(st.time, sim->cosmo);
+        }
+        st.n_steps += 1;                                                         // :635 / :797
+    }
+    return result;
+}
+
+int msm_sim_state(const msm_sim* sim, int32_t s, msm_stream_state* out) {
+    if (!sim || !out || s < 0 || s >= sim->p.n_streams) return MSM_E_ARG;
+    const Stream& st = sim->st[s];
+    out->time = st.time;
+    out->tau = st.tau;
+    out->dt = st.dt;
+    out->potential_max = st.potential_max;
+    out->alias_mass = st.alias_mass;
+    out->scale_factor = sim->p.expanding ? st.solver.get_a() : 1.0;
+    out->n_steps = st.n_steps;
+    out->current_dumps = st.current_dumps;
+    out->dumped = st.dumped;
+    out->finished = not_finished(sim, st) ? 0 : 1;
+    out->aliased = st.aliased;
+    return MSM_OK;
+}
+
+int msm_sim_get_psi(msm_sim* sim, int32_t stream, double* re, double* im) {
+    if (!sim) return MSM_E_ARG;
+    int rc = msm_get_psi(sim->ctx, stream, re, im);
+    if (rc) sim->err = msm_last_error(sim->ctx);
+    return rc;
+}
+
+int msm_sim_dump(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index) {
+    if (!sim || !root_dir || !sim_name) return MSM_E_ARG;
+    const int dims = sim->p.dims, n = sim->p.size;
+    size_t count = 1;
+    for (int d = 0; d < dims; ++d) count *= (size_t)n;
+    // at most 2 * MAX_CONCURRENT_GRID_WRITES live writers (simulation_object.rs:39,:1123)
+    if (sim->io.size() >= 32) msm_sim_wait_io(sim);
+    std::vector<double>* re = new std::vector<double>(count);
+    std::vector<double>* im = new std::vector<double>(count);
+    int rc = msm_get_psi(sim->ctx, stream, re->data(), im->data());
+    if (rc) {
+        sim->err = msm_last_error(sim->ctx);
+        delete re;
+        delete im;
+        return rc;
+    }
+    const std::string dir = std::string(root_dir) + "/" + sim_name;
+    mkdirs(dir);                                                                 // :1119
+    char base[64];
+    snprintf(base, sizeof base, "/psi_%05u", dump_index);                        // :1155-1158
+    const std::string pr = dir + base + "_real", pi = dir + base + "_imag";      // io.rs:54-55
+    sim->io.emplace_back([=]() { write_npy(pr, re->data(), dims, n); delete re; });
+    sim->io.emplace_back([=]() { write_npy(pi, im->data(), dims, n); delete im; });
+    return MSM_OK;
+}
+
+}  // extern "C"

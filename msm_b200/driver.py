@@ -1,0 +1,99 @@
+"""Host driver: `python -m msm_b200 --toml X` mirrors `msm-simulator --toml X` (simulator/src/main.rs:21-89).
+
+The reference runs the streams of a TOML one after another (main.rs:43); here all streams of this rank are resident
+on the GPU and advance together, each with its own adaptive time step and dump schedule.  Dumps use the reference's
+on-disk layout `sim-data/<sim>[-stream%05d]/psi_%05d_real|_imag` (simulation_object.rs:1155-1158), so
+`msm-synthesizer` and the plotting scripts keep working.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from .api import COUPLING_INDEPENDENT, SimulationObject
+from .config import RunConfig, read_toml
+
+
+def shard_streams(n_streams: int, rank: int, nranks: int) -> List[int]:
+    """Stream indices owned by `rank`: round-robin, so the trailing mean-field run lands on the least loaded rank."""
+    return [s for s in range(n_streams) if s % nranks == rank]
+
+
+def load_initial_conditions(sim: SimulationObject, cfg: RunConfig, local: List[int], base_dir: str = ".") -> None:
+    """`new_from_params` (simulation_object.rs:404-435): build the IC of every local stream, then apply the sampler."""
+    p = cfg.parameters
+    ics = cfg.ics
+    g = sim.grid
+    kind = ics["type"]
+    for li, s in enumerate(local):
+        if li == 0:
+            if kind == "UserSpecified":                              # ics.rs:650-730
+                z = np.load(os.path.join(base_dir, ics["path"]))
+                re_, im_ = np.asarray(z["real"], np.float64), np.asarray(z["imag"], np.float64)
+                if re_.ndim != p.dims or any(v != p.size for v in re_.shape):
+                    raise ValueError("user-provided data does not match dims/size of the toml")
+                g.set_psi_planes(0, re_, im_)
+            elif kind == "ColdGauss":                                # ics.rs:24-162
+                g.ic_cold_gauss(0, [float(v) for v in ics["mean"]], [float(v) for v in ics["std"]])
+            elif kind == "SphericalTophat":                          # ics.rs:165-280
+                g.ic_spherical_tophat(0, p.axis_length, float(ics["radius"]), float(ics["delta"]), float(ics["slope"]))
+            else:
+                raise NotImplementedError(f"ics type {kind} is not available on device")
+        else:
+            g.ic_copy(li, 0)
+    for li, s in enumerate(local):                                   # ics.rs:434-648
+        spec = cfg.streams[s]
+        if spec.seed is not None:
+            g.sample_perturbation(li, spec.scheme, spec.seed, cfg.n_tot)
+
+
+def run(cfg: RunConfig, out_root: str = "sim-data", rank: int = 0, nranks: int = 1, device: int = 0,
+        base_dir: str = ".", verbose: bool = False, write: bool = True, max_updates: Optional[int] = None) -> dict:
+    local = shard_streams(len(cfg.streams), rank, nranks)
+    sim = SimulationObject(cfg.parameters, n_streams=len(local), coupling=COUPLING_INDEPENDENT, device=device)
+    load_initial_conditions(sim, cfg, local, base_dir)
+    t0 = time.time()
+    if write:
+        for li, s in enumerate(local):                               # main.rs:61 dump the initial condition
+            sim.dump(li, out_root, cfg.streams[s].sim_name, 0)
+    updates = 0
+    while sim.not_finished() and (max_updates is None or updates < max_updates):   # main.rs:65-69
+        sim.update()
+        updates += 1
+        for li, s in enumerate(local):
+            st = sim.state(li)
+            if st.dumped and write:
+                sim.dump(li, out_root, cfg.streams[s].sim_name, st.current_dumps)
+    sim.wait_io()
+    steps = sum(int(sim.state(li).n_steps) for li in range(len(local)))
+    wall = time.time() - t0
+    if verbose:
+        print(f"rank {rank}: {len(local)} streams, {steps} stream-steps in {wall:.2f} s")
+    sim.close()
+    return {"streams": len(local), "stream_steps": steps, "seconds": wall}
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="msm_b200", description="B200-native msm-simulator time-evolution loop")
+    ap.add_argument("--toml", "-t", required=True)
+    ap.add_argument("--verbose", "-v", action="store_true")
+    ap.add_argument("--test", action="store_true", help="construct the streams and exit (main.rs:59)")
+    ap.add_argument("--out", default="sim-data")
+    ap.add_argument("--static", action="store_true", help="ignore [cosmology] (cargo feature `expanding` off)")
+    args = ap.parse_args(argv)
+    cfg = read_toml(args.toml, expanding=False if args.static else None)
+    rank = int(os.environ.get("RANK", "0"))
+    nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    base_dir = os.path.dirname(os.path.abspath(args.toml))
+    # the reference resolves IC paths relative to the working directory
+    base_dir = "." if os.path.exists(cfg.ics.get("path", "")) else os.path.dirname(base_dir)
+    res = run(cfg, args.out, rank, nranks, device, base_dir, args.verbose, write=not args.test,
+              max_updates=0 if args.test else None)
+    if args.verbose or len(cfg.streams) > 1:
+        print(f"Finished all streams in {res['seconds']:.0f} seconds")
+    return 0
