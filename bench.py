@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the MSM time-evolution loop on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W          (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W  (the reference's CPU algorithm on the host cores)
+
+Metric (BASELINE.json): cell-updates/s = cells x streams x steps / seconds of the step loop, where one step is
+one `SimulationObject::update()` (simulation_object.rs:475-661) of every stream: potential at t, adaptive dt (host
+sync), drift, inverse FFT, potential, kick, forward FFT, drift, alias check (host sync).
+Workload: BASELINE.json configs[4] -- synthetic 512^3 x 64 streams, fp64, physical scalars and ColdGauss base field
+of examples/gaussian-overdensity-mft.toml, per-stream Wigner noise (seed = stream id), static box, independent
+streams (the reference's semantics), stream-sharded across the ranks (64 / N each, no data-path collective).
+Every stream is 2 GiB >> 126 MB of L2, so no L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_CELL_UPDATE = 480.0       # DESIGN.md section 4 (independent streams)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="msm_b200", choices=["msm_b200", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--streams", type=int, default=64, help="total streams over all ranks")
+    ap.add_argument("--chunk", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_params(size):
+    """examples/gaussian-overdensity-mft.toml resolved (tests/golden/configs.json holds the same numbers)."""
+    import msm_b200 as m
+    hbar_ = 0.02
+    return m.SimulationParameters(axis_length=30.0, final_sim_time=400.0, cfl=0.02, num_data_dumps=200,
+                                  total_mass=1e10, particle_mass=1.757e-90 / hbar_, hbar_=hbar_, k2_cutoff=0.95,
+                                  alias_threshold=0.02, dims=3, size=size, time=0.0, cosmology=None)
+
+
+N_TOT_SAMPLER = 1e10        # Wigner noise with n_tot = 1e10
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_step_rate(size, steps, warmup):
+    """The oracle's un-fused 7-FFT update() (the reference's algorithm) on the host cores: cell-updates/s."""
+    from oracle import msm_oracle as o
+    hbar_ = 0.02
+    p = o.SimulationParameters(axis_length=30.0, time=0.0, final_sim_time=400.0, cfl=0.02, num_data_dumps=200,
+                               total_mass=1e10, particle_mass=o.HBAR / hbar_, sim_name="bench", k2_cutoff=0.95,
+                               alias_threshold=0.02, hbar_=hbar_, dims=3, size=size,
+                               ics={"type": "ColdGauss", "mean": [15.0] * 3, "std": [10.0] * 3})
+    psi0 = o.cold_gauss([15.0] * 3, [10.0] * 3, p)
+    sim = o.SimulationObject(p, psi0)
+    for _ in range(warmup):
+        sim.update()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.update()
+    dt = time.perf_counter() - t0
+    return size ** 3 * steps / dt, dt / steps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (oracle restatement: the Rust/ArrayFire binary cannot be
+    built here) with all host threads.  Each step = one update() of ONE stream on a bounded grid."""
+    if rank != 0:
+        return
+    from oracle import msm_oracle as o
+    cores = os.cpu_count() or 1
+    o.set_workers(cores)
+    size = args.cpu_size or 256
+    rate, sec = cpu_step_rate(size, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "cell-updates/s", "value": rate, "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.size}^3 x {args.streams} streams fp64 static box"},
+            "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                             "sample": f"1 stream x {size}^3 per step, NumPy/pocketfft restatement of update()"},
+            "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def build_streams(sim, n_local, first_global, size):
+    g = sim.grid
+    g.ic_cold_gauss(0, [15.0] * 3, [10.0] * 3)
+    for s in range(1, n_local):
+        g.ic_copy(s, 0)
+    for s in range(n_local):
+        g.sample_perturbation(s, "Wigner", first_global + s + 1, N_TOT_SAMPLER)
+    g.synchronize()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import msm_b200 as m
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    n_total = args.streams
+    if n_total % world:
+        raise SystemExit("--streams must be divisible by the number of ranks")
+    n_local = n_total // world
+    size = args.size
+    cells = size ** 3
+    params = workload_params(size)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident run: streams generated on the device, timed with CUDA events on the library's stream ----------
+    sim = None
+    note = ""
+    for chunk in (args.chunk, 4, 2):
+        try:
+            sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk)
+            break
+        except m.MsmError as e:
+            if e.code != -7:
+                raise
+            note = f"chunk {chunk} did not fit"
+    if sim is None:
+        raise SystemExit("streams do not fit in device memory: " + note)
+    g = sim.grid
+    build_streams(sim, n_local, rank * n_local, size)
+    for _ in range(args.warmup):
+        sim.update()
+    g.synchronize()
+    launches0 = g.launch_count()
+    g.profile_enable(True)
+    clocks = ClockSampler(device)
+    clocks.start()
+    barrier()
+    g.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.update()
+    ms = g.timer_stop()
+    wall = time.perf_counter() - t0
+    barrier()
+    clk = clocks.stop()
+    launches = g.launch_count() - launches0
+    prof = g.profile_read()
+    g.profile_enable(False)
+    ms = max_over_ranks(ms)
+    value = cells * n_total * args.steps / (ms * 1e-3)
+    st = sim.state(0)
+    assert st.n_steps == args.warmup + args.steps and not st.aliased
+
+    # ---- roofline of the dominant kernel (CUDA events around every launch, same timed region) ------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    fft = [r for r in prof if r["name"].startswith("fft_pass")]
+    top = max(fft, key=lambda r: r["ms_total"])
+    ach = top["algorithmic_bytes"] / (top["ms_total"] * 1e-3) / 1e9
+    kernel_ms = sum(r["ms_total"] for r in prof)
+    roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": top["ms_total"] / top["launches"], "share_of_step": top["ms_total"] / kernel_ms,
+                "step": {"algorithmic_bytes_per_cell_update": ALG_BYTES_PER_CELL_UPDATE,
+                         "achieved": value * ALG_BYTES_PER_CELL_UPDATE / 1e9, "frac": value * ALG_BYTES_PER_CELL_UPDATE / 1e9 / peak,
+                         "frac_of_8TBps": value * ALG_BYTES_PER_CELL_UPDATE / 8e12},
+                "kernels": [{"name": r["name"], "launches": r["launches"], "ms": round(r["ms_total"], 3),
+                             "GBps": round(r["algorithmic_bytes"] / (r["ms_total"] * 1e-3) / 1e9, 1)}
+                            for r in sorted(prof, key=lambda r: -r["ms_total"])]}
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(2 * cells, dtype=torch.float64, pin_memory=True)
+        out_re = torch.empty(cells, dtype=torch.float64, pin_memory=True)
+        out_im = torch.empty(cells, dtype=torch.float64, pin_memory=True)
+        hnp, renp, imnp = host.numpy(), out_re.numpy(), out_im.numpy()
+        hnp[:] = g.get_psi(0).reshape(-1).view(np.float64)        # a realistic wavefunction as the host-side IC
+        sim.close()
+        sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk)
+        g = sim.grid
+        import ctypes as C
+        from msm_b200._lib import lib, check
+        dp = C.POINTER(C.c_double)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(n_local):                                   # H2D of every stream's IC from pinned memory
+            check(lib.msm_sim_set_psi(sim.handle, s, hnp.ctypes.data_as(dp)), sim.handle, sim=True)
+        for _ in range(args.steps):
+            sim.update()
+        for s in range(n_local):                                   # one dump: D2H of every stream, re/im planes
+            check(lib.msm_sim_get_psi(sim.handle, s, renp.ctypes.data_as(dp), imnp.ctypes.data_as(dp)), sim.handle, sim=True)
+        sec = time.perf_counter() - t0
+        barrier()
+        sec = max_over_ranks(sec)
+        tab = 16 * size * n_local
+        e2e = {"value": cells * n_total * args.steps / sec, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": int(16 * cells * n_local / args.steps + tab + 16 * n_local),
+               "d2h_bytes_per_step": int(16 * cells * n_local / args.steps + 16 * n_local),
+               "seconds": sec, "what": "msm_sim_set_psi of all streams from pinned host memory + K x msm_sim_update "
+               "+ msm_sim_get_psi of all streams (one dump) inside the timed region"}
+    sim.close()
+
+    # ---- the reference's CPU algorithm beside it (rank 0, N = 1 only) ------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import msm_oracle as o
+        cores = os.cpu_count() or 1
+        o.set_workers(cores)
+        csize = args.cpu_size or 256
+        rate, sec = cpu_step_rate(csize, 2, 1)
+        cpu = {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+               "sample": f"1 stream x {csize}^3, 2 update() after 1 warm-up ({sec:.2f} s/step), NumPy/pocketfft "
+                         "restatement of the reference's un-fused 7-FFT step"}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"synthetic {size}^3 x {n_total} streams fp64 static box (BASELINE configs[4])",
+                           "streams_per_gpu": n_local, "coupling": "independent", "chunk_streams": chunk,
+                           "l2": "inputs larger than L2 (2 GiB per stream vs 126 MB)",
+                           "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -161,6 +161,9 @@ typedef struct msm_profile_record {
 } msm_profile_record;
 int msm_profile_enable(msm_ctx* ctx, int32_t on);
 int msm_profile_read(msm_ctx* ctx, msm_profile_record* out, int32_t cap, int32_t* n_out);
+/* CUDA-event stopwatch on the context's own stream (torch.cuda.Event would only see torch's stream). */
+int msm_timer_start(msm_ctx* ctx);
+int msm_timer_stop(msm_ctx* ctx, double* elapsed_ms);   /* records, synchronises, returns the elapsed time */
 /* Number of kernel launches issued by this context so far. */
 int msm_launch_count(const msm_ctx* ctx, uint64_t* launches);
 

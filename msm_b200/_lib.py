@@ -95,6 +95,8 @@ PROTOTYPES = {
     "msm_sample_perturbation": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_double]),
     "msm_profile_enable": (C.c_int, [_vp, C.c_int32]),
     "msm_profile_read": (C.c_int, [_vp, C.POINTER(MsmProfileRecord), C.c_int32, _ip]),
+    "msm_timer_start": (C.c_int, [_vp]),
+    "msm_timer_stop": (C.c_int, [_vp, _dp]),
     "msm_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "msm_sim_create": (C.c_int, [C.POINTER(MsmSimParams), C.POINTER(_vp)]),
     "msm_sim_destroy": (None, [_vp]),

@@ -209,6 +209,14 @@ class Context:
         return [dict(name=recs[i].name.decode(), launches=int(recs[i].launches), ms_total=float(recs[i].ms_total),
                      algorithmic_bytes=float(recs[i].algorithmic_bytes)) for i in range(n.value)]
 
+    def timer_start(self) -> None:
+        self._chk(lib.msm_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        v = C.c_double()
+        self._chk(lib.msm_timer_stop(self.handle, C.byref(v)))
+        return v.value
+
     def launch_count(self) -> int:
         v = C.c_uint64()
         self._chk(lib.msm_launch_count(self.handle, C.byref(v)))

@@ -253,6 +253,7 @@ struct msm_ctx {
     int ntiles_last = 0;
     uint64_t bytes = 0, launches = 0;
     void* comm = nullptr;
+    cudaEvent_t tm_a = nullptr, tm_b = nullptr;
     // profiling
     bool prof = false;
     std::vector<ProfEvent> prof_pending;
@@ -673,6 +674,8 @@ void msm_destroy(msm_ctx* ctx) {
     if (ctx->h_dtab) cudaFreeHost(ctx->h_dtab);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->dtab_done) cudaEventDestroy(ctx->dtab_done);
+    if (ctx->tm_a) cudaEventDestroy(ctx->tm_a);
+    if (ctx->tm_b) cudaEventDestroy(ctx->tm_b);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -1120,6 +1123,29 @@ int msm_profile_read(msm_ctx* ctx, msm_profile_record* out, int32_t cap, int32_t
         ++k;
     }
     *n_out = k;
+    return MSM_OK;
+}
+
+int msm_timer_start(msm_ctx* ctx) {
+    if (!ctx) return MSM_E_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->tm_a) {
+        CU(cudaEventCreate(&ctx->tm_a));
+        CU(cudaEventCreate(&ctx->tm_b));
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaEventRecord(ctx->tm_a, ctx->st));
+    return MSM_OK;
+}
+
+int msm_timer_stop(msm_ctx* ctx, double* elapsed_ms) {
+    if (!ctx || !elapsed_ms || !ctx->tm_a) return fail(ctx, MSM_E_ARG, "msm_timer_stop: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaEventRecord(ctx->tm_b, ctx->st));
+    CU(cudaEventSynchronize(ctx->tm_b));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->tm_a, ctx->tm_b));
+    *elapsed_ms = ms;
     return MSM_OK;
 }
 

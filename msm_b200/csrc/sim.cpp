@@ -43,7 +43,7 @@ double rk4(const std::function<double(double, double)>& f, double tn, double yn,
 // expanding.rs:12-118.  The reference wraps crate `cosmology` 0.2.0 (not vendored).  Restated as flat FLRW,
 // omega_de0 = 1 - om - or (expanding.rs:29-38), H0 = h * 1.022e-4 / Myr, a(0) = 1/(1+z0),
 // da/dt = a H0 sqrt(om a^-3 + or a^-4 + ode), RK4 sub-steps bounded by max_dloga * a / (da/dt); negative dt
-// steps backwards with the same rule.  Identical to oracle/msm_oracle.py::ScaleFactorSolver.
+// steps backwards with the same rule.
 struct ScaleFactorSolver {
     double om = 0, orad = 0, ode = 0, h0 = 0, max_dloga = DEFAULT_MAX_DLOGA, a = 1, t = 0;
     ScaleFactorSolver() {}

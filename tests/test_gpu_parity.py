@@ -1,0 +1,418 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run on a B200: pytest -m gpu.
+
+Tolerances (fp64, relative L2 unless noted; measured values are ~1e-15):
+  one FFT vs pocketfft            <= 1e-13
+  phi, psi, psi_k after one step  <= 1e-12
+  dt / dtau, time, tau            <= 1e-13 relative
+  max|phi|                        <= 1e-12 relative
+  alias mass                      <= 1e-10 relative or 1e-30 absolute (it is round-off noise when nothing aliases)
+  trajectories (up to 200 steps)  <= 1e-10   (the north-star bound)
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.fft as sf
+
+import msm_b200 as m
+from msm_b200 import _lib
+from oracle import msm_oracle as o
+from conftest import rel_l2
+from golden_util import GOLDEN, initial_wavefunction, oracle_streams, to_msm_params
+
+pytestmark = pytest.mark.gpu
+
+
+def alias_close(a, b):
+    return abs(a - b) <= max(1e-10 * abs(b), 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FFT layer (utils/fft.rs) -- rows a3, a4
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [1, 2, 3])
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024])
+def test_fft_matches_pocketfft(dims, n):
+    if n ** dims > 2 ** 24:
+        pytest.skip("covered by the large-grid property tests")
+    rng = np.random.default_rng(n * 10 + dims)
+    batch = 3
+    a = rng.standard_normal((batch,) + (n,) * dims) + 1j * rng.standard_normal((batch,) + (n,) * dims)
+    f = m.forward(a, dims)
+    ref = sf.fftn(a, axes=tuple(range(1, dims + 1)), norm="ortho")
+    assert rel_l2(f, ref) < 1e-13
+    assert rel_l2(m.inverse(f, dims), a) < 1e-13
+    ib = m.inverse(a, dims)
+    assert rel_l2(ib, sf.ifftn(a, axes=tuple(range(1, dims + 1)), norm="ortho")) < 1e-13
+
+
+@pytest.mark.parametrize("K,S,value,length", [(1, 8, complex(0.0, 128.0 ** -0.5), 128.0), (1, 2, 2j, None),
+                                              (2, 2, 2j, None), (3, 2, 2j, None), (2, 8, 2j, None), (3, 8, 2j, None)])
+def test_reference_fft_round_trips(K, S, value, length):
+    # simulator/tests/fft.rs:2-601
+    values = np.full((S,) * K, value, dtype=np.complex128)
+    fk = m.forward(values)
+    if length is not None:
+        assert o.check_norm(fk, length / S, K)
+    assert abs(np.sum(np.abs(fk) ** 2) - np.sum(np.abs(values) ** 2)) < 1e-12 * values.size
+    assert np.sum(np.abs(m.inverse(fk) - values)) < 1e-12
+
+
+def test_fft_ragged_batches():
+    rng = np.random.default_rng(5)
+    for batch in (1, 2, 5, 9, 17):          # odd groups, more than one chunk
+        a = rng.standard_normal((batch, 16, 16, 16)) + 1j * rng.standard_normal((batch, 16, 16, 16))
+        assert rel_l2(m.forward(a, 3), sf.fftn(a, axes=(1, 2, 3), norm="ortho")) < 1e-13
+
+
+def test_spec_grid_bit_exact():
+    # utils/fft.rs:185-214 demands equality, not closeness
+    for dims in (1, 2, 3):
+        for n, dx in ((4, 0.25), (16, 30.0 / 16), (64, 0.1437)):
+            assert np.array_equal(m.spec_grid(dx, dims, n), o.spec_grid(dx, dims, n))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# grid level: potential, one step  -- rows a5, a6, a9, a10, a12
+# ---------------------------------------------------------------------------------------------------------------
+def make_ctx(p, n_streams, **kw):
+    sim = o.SimulationObject(p, np.zeros((p.size,) * p.dims, dtype=np.complex128))
+    return m.Context(p.dims, p.size, n_streams, p.dx, sim.density_prefactor(), sim.poisson_coeff(), p.k2_cutoff, **kw)
+
+
+@pytest.mark.parametrize("name,size", [("spherical-tophat", None), ("spherical-tophat", 32),
+                                       ("spherical-tophat-cosmo", None), ("repro-planeWave1d", None)])
+def test_potential_matches_oracle(name, size):
+    ps = oracle_streams(name, size, limit=3)
+    ctx = make_ctx(ps[0], len(ps))
+    sims = []
+    for i, p in enumerate(ps):
+        psi0 = initial_wavefunction(p)
+        ctx.set_psi(i, psi0)
+        s = o.SimulationObject(p, psi0)
+        s.calculate_potential()
+        sims.append(s)
+    pm = ctx.potential_max()
+    for i, s in enumerate(sims):
+        want = np.max(np.abs(s.phi))
+        assert abs(pm[i] - want) <= 1e-12 * want
+        phi = ctx.get_potential(i)
+        assert rel_l2(phi, s.phi.real) < 1e-12
+    ctx.close()
+
+
+def test_single_step_fields_match_oracle():
+    ps = oracle_streams("spherical-tophat", limit=4)
+    ctx = make_ctx(ps[0], len(ps))
+    sims = []
+    for i, p in enumerate(ps):
+        psi0 = initial_wavefunction(p)
+        ctx.set_psi(i, psi0)
+        sims.append(o.SimulationObject(p, psi0))
+    dts = np.array([0.05, 0.11, 0.2, 0.31])       # different dt per stream
+    hb = ps[0].hbar_
+    for i, s in enumerate(sims):                  # the oracle's step with a forced dt
+        s.psik = o.forward(s.psi)
+        kev = np.exp(complex(0, -dts[i] / 4.0 * hb) * s.parameters.spec_grid)
+        s.psik = s.psik * kev
+        s.psi = o.inverse(s.psik)
+        s.calculate_potential()
+        s.psi = s.psi * np.exp(complex(0, -dts[i] / hb) * s.phi)
+        s.psik = o.forward(s.psi) * kev
+        s.psi = o.inverse(s.psik)
+        s.check_alias()
+    alias = ctx.step(dts * hb / 4.0, dts / hb)
+    for i, s in enumerate(sims):
+        assert rel_l2(ctx.get_psik(i), s.psik) < 1e-12
+        assert rel_l2(ctx.get_psi(i), s.psi) < 1e-12
+        re, im = ctx.get_psi_planes(i)
+        assert np.array_equal(re + 1j * im, ctx.get_psi(i))
+        assert alias_close(alias[i], s.last_alias_mass)
+    ctx.close()
+
+
+def test_alias_mass_when_power_sits_above_the_cutoff():
+    """A wavefunction with real power beyond k2_cutoff: the masked sum must match to 1e-10 (not just be ~0)."""
+    p = oracle_streams("spherical-tophat", limit=1)[0]
+    p.k2_cutoff = 0.3
+    p.__post_init__()
+    rng = np.random.default_rng(3)
+    psi0 = o.normalize(rng.standard_normal((16,) * 3) + 1j * rng.standard_normal((16,) * 3), p.dx, 3)
+    ctx = make_ctx(p, 1)
+    ctx.set_psi(0, psi0)
+    s = o.SimulationObject(p, psi0)
+    s.psik = o.forward(psi0)
+    s.check_alias()
+    alias = ctx.step(np.zeros(1), np.zeros(1))     # zero dt: psi_k unchanged, alias of the IC
+    assert s.last_alias_mass > 0.1
+    assert abs(alias[0] - s.last_alias_mass) < 1e-12 * s.last_alias_mass
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-logic level: trajectories -- rows a7, a8, a11, a13, a15, a16
+# ---------------------------------------------------------------------------------------------------------------
+def run_both(ps, steps, coupling=m.COUPLING_INDEPENDENT, chunk=0, psi0s=None):
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=len(ps), coupling=coupling, chunk_streams=chunk)
+    refs = []
+    for i, p in enumerate(ps):
+        psi0 = initial_wavefunction(p) if psi0s is None else psi0s[i]
+        sim.set_psi(i, psi0)
+        refs.append(o.SimulationObject(p, psi0))
+    worst = 0.0
+    for k in range(steps):
+        if not sim.not_finished():
+            break
+        sim.update()
+        for i, r in enumerate(refs):
+            if not r.not_finished():
+                continue
+            r.update()
+            st = sim.state(i)
+            assert abs(st.dt - r.last_dt) <= 1e-13 * abs(r.last_dt), (k, i, st.dt, r.last_dt)
+            assert abs(st.time - r.parameters.time) <= 1e-13 * abs(r.parameters.time)
+            assert abs(st.potential_max - r.last_potential_max) <= 1e-12 * r.last_potential_max
+            assert alias_close(st.alias_mass, r.last_alias_mass)
+            assert st.current_dumps == r.parameters.current_dumps and st.n_steps == r.parameters.n_steps
+            if ps[0].expanding:
+                assert abs(st.tau - r.parameters.tau) <= 1e-13 * abs(r.parameters.tau)
+                assert abs(st.scale_factor - r.scale_factor_solver.get_a()) <= 1e-14
+            if k % 4 == 3 or k == steps - 1:
+                worst = max(worst, rel_l2(sim.get_psi(i), r.psi))
+    return sim, refs, worst
+
+
+@pytest.mark.parametrize("name,size,nstreams,steps", [
+    ("spherical-tophat", None, 3, 12), ("spherical-tophat-cosmo", None, 3, 12), ("planeWave3d_e10_sym", None, 3, 12),
+    ("spherical-tophat", 32, 2, 6), ("spherical-tophat", 64, 2, 4), ("gaussian-overdensity-mft", 64, 1, 4),
+    ("repro-planeWave1d", None, 3, 8), ("spherical-tophat", 4, 2, 3), ("spherical-tophat", 8, 3, 3),
+])
+def test_trajectory_matches_oracle(name, size, nstreams, steps):
+    ps = oracle_streams(name, size, limit=nstreams)
+    sim, refs, worst = run_both(ps, steps)
+    assert worst < 1e-10, worst
+    sim.close()
+
+
+def test_two_dimensional_grid():
+    t = __import__("golden_util").load_toml("spherical-tophat", 32)
+    t.dims = 2
+    ps = list(o.simulation_iter(t))[:3]
+    sim, refs, worst = run_both(ps, 5)
+    assert worst < 1e-10
+    sim.close()
+
+
+@pytest.mark.parametrize("name", ["spherical-tophat", "spherical-tophat-cosmo", "planeWave3d_e10_sym"])
+def test_against_committed_golden_trajectories(name):
+    z = np.load(f"{GOLDEN}/traj_{name}.npz")
+    its = oracle_streams(name)
+    ps = [next(q for q in its if q.sim_name == str(s)) for s in z["streams"]]
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=len(ps))
+    for j in range(len(ps)):
+        sim.set_psi(j, z[f"s{j}_psi0"])
+    for step in range(1, 26):
+        sim.update()
+        for j in range(len(ps)):
+            row = z[f"s{j}_scalars"][step - 1]
+            st = sim.state(j)
+            assert abs(st.dt - row[0]) <= 1e-13 * abs(row[0])
+            assert abs(st.potential_max - row[1]) <= 1e-12 * abs(row[1])
+            assert alias_close(st.alias_mass, row[2])
+            assert abs(st.time - row[3]) <= 1e-13 * abs(row[3])
+            assert st.current_dumps == int(row[5])
+            key = f"s{j}_psi_{step}"
+            if key in z.files:
+                assert rel_l2(sim.get_psi(j), z[key]) < 1e-10
+    sim.close()
+
+
+def test_full_run_to_final_time_with_dumps(tmp_path):
+    """examples/spherical-tophat.toml to t = final (200 steps, 200 dumps) for one sampled stream + the MFT run:
+    every dump compared; on-disk layout of utils/io.rs:34-88 checked."""
+    its = oracle_streams("spherical-tophat")
+    ps = [its[0], its[-1]]
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=2)
+    refs = []
+    for i, p in enumerate(ps):
+        psi0 = initial_wavefunction(p)
+        sim.set_psi(i, psi0)
+        refs.append(o.SimulationObject(p, psi0))
+    worst, steps = 0.0, 0
+    while sim.not_finished():
+        sim.update()
+        steps += 1
+        for i, r in enumerate(refs):
+            r.update()
+            st = sim.state(i)
+            assert st.dumped == 1 and st.current_dumps == r.parameters.current_dumps
+            if st.current_dumps % 20 == 0:
+                worst = max(worst, rel_l2(sim.get_psi(i), r.psi))
+                sim.dump(i, str(tmp_path), ps[i].sim_name, st.current_dumps)
+    sim.wait_io()
+    assert steps == 200 and not any(r.not_finished() for r in refs)
+    assert sim.state(0).finished == 1 and sim.state(0).time == 40.0
+    assert worst < 1e-10, worst
+    d = tmp_path / ps[0].sim_name
+    re = np.load(open(d / "psi_00200_real", "rb"))       # extension-less NPY, shape (n, n, n, 1), f64
+    im = np.load(open(d / "psi_00200_imag", "rb"))
+    assert re.shape == (16, 16, 16, 1) and re.dtype == np.float64
+    assert rel_l2(re[..., 0] + 1j * im[..., 0], refs[0].psi) < 1e-10
+    sim.close()
+
+
+@pytest.mark.parametrize("nstreams,chunk", [(1, 0), (3, 2), (5, 4), (7, 2), (11, 8), (9, 0)])
+def test_odd_stream_counts_and_chunking(nstreams, chunk):
+    its = oracle_streams("spherical-tophat")
+    ps = its[:nstreams]
+    sim, refs, worst = run_both(ps, 3, chunk=chunk)
+    assert worst < 1e-10
+    sim.close()
+
+
+def test_streams_finish_at_different_steps():
+    """Streams with different adaptive dt take different numbers of steps per dump; finished streams are masked."""
+    its = oracle_streams("gaussian-overdensity-mft", 16, limit=1)
+    p = its[0]
+    p.final_sim_time, p.num_data_dumps = 6.0, 3
+    ps = [p, o.SimulationParameters(**{**{f: getattr(p, f) for f in ("axis_length", "time", "final_sim_time", "cfl",
+          "num_data_dumps", "total_mass", "particle_mass", "k2_cutoff", "alias_threshold", "hbar_", "dims", "size")},
+          "sim_name": "b", "ics": p.ics})]
+    base = initial_wavefunction(p)
+    rng = np.random.default_rng(0)
+    psi_b = o.normalize(base * (1.0 + 3.0 * rng.random(base.shape)), p.dx, 3)    # deeper potential => smaller dt
+    sim, refs, worst = run_both(ps, 200, psi0s=[base, psi_b])
+    assert not sim.not_finished() and all(not r.not_finished() for r in refs)
+    assert sim.state(0).n_steps == refs[0].parameters.n_steps != refs[1].parameters.n_steps == sim.state(1).n_steps
+    for i, r in enumerate(refs):
+        assert rel_l2(sim.get_psi(i), r.psi) < 1e-10
+    sim.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# coupled (summed-density) mode -- north-star variant
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,nstreams", [("spherical-tophat", 4), ("spherical-tophat", 5), ("spherical-tophat-cosmo", 3)])
+def test_summed_mode_matches_oracle(name, nstreams):
+    ps = oracle_streams(name, limit=nstreams)
+    psi0s = [initial_wavefunction(p) for p in ps]
+    ens = o.SummedEnsemble(ps[0], psi0s)
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=nstreams, coupling=m.COUPLING_SUMMED, chunk_streams=2)
+    for i, a in enumerate(psi0s):
+        sim.set_psi(i, a)
+    for k in range(5):
+        sim.update()
+        ens.update()
+        st = sim.state(0)
+        assert abs(st.dt - ens.head.last_dt) <= 1e-13 * ens.head.last_dt
+        assert abs(st.time - ens.head.parameters.time) <= 1e-13 * ens.head.parameters.time
+    for i in range(nstreams):
+        assert rel_l2(sim.get_psi(i), ens.streams[i].psi) < 1e-10
+        assert alias_close(sim.state(i).alias_mass, ens.streams[i].last_alias_mass)
+    sim.close()
+
+
+def test_summed_mode_with_identical_streams_equals_independent():
+    p = oracle_streams("spherical-tophat")[-1]
+    psi0 = initial_wavefunction(p)
+    a = m.SimulationObject(to_msm_params(p), n_streams=4, coupling=m.COUPLING_SUMMED)
+    b = m.SimulationObject(to_msm_params(p), n_streams=1)
+    for i in range(4):
+        a.set_psi(i, psi0)
+    b.set_psi(0, psi0)
+    for _ in range(4):
+        a.update()
+        b.update()
+    assert rel_l2(a.get_psi(3), b.get_psi(0)) < 1e-12
+    assert abs(a.state(2).dt - b.state(0).dt) <= 1e-13 * b.state(0).dt
+    a.close()
+    b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# on-device initial conditions (row f-1) and errors
+# ---------------------------------------------------------------------------------------------------------------
+def test_device_initial_conditions_match_oracle():
+    p = oracle_streams("spherical-tophat", limit=1)[0]
+    ctx = make_ctx(p, 2)
+    ctx.ic_spherical_tophat(0, p.axis_length, 5.0, 100.0, 50.0)
+    base = o.spherical_tophat(p, 5.0, 100.0, 50.0)
+    assert rel_l2(ctx.get_psi(0), base) < 1e-13
+    ctx.ic_copy(1, 0)
+    ctx.sample_perturbation(1, "Husimi", 7, p.n_tot)
+    want = o.sample_quantum_perturbation(base, p, {"seed": 7, "scheme": "Husimi"})
+    assert rel_l2(ctx.get_psi(1), want) < 1e-13
+    ctx.sample_perturbation(0, "Wigner", 2 ** 40 + 3, p.n_tot)
+    want = o.sample_quantum_perturbation(base, p, {"seed": 2 ** 40 + 3, "scheme": "Wigner"})
+    assert rel_l2(ctx.get_psi(0), want) < 1e-13
+    ctx.close()
+    g = oracle_streams("gaussian-overdensity-mft", 32, limit=1)[0]
+    ctx = make_ctx(g, 1)
+    ctx.ic_cold_gauss(0, [15.0] * 3, [10.0] * 3)
+    assert rel_l2(ctx.get_psi(0), o.cold_gauss([15.0] * 3, [10.0] * 3, g)) < 1e-13
+    ctx.close()
+
+
+def test_error_behaviour():
+    p = oracle_streams("spherical-tophat", limit=1)[0]
+    ctx = make_ctx(p, 2)
+    with pytest.raises(m.MsmError) as ei:                  # no psi yet
+        ctx.potential_max()
+    assert ei.value.code == _lib.MSM_E_STATE
+    with pytest.raises(m.MsmError) as ei:
+        ctx.get_psi(5)
+    assert ei.value.code == _lib.MSM_E_ARG
+    ctx.close()
+    # aliasing is reported per stream, the reference panics (simulation_object.rs:607-617)
+    p.alias_threshold = 1e-40
+    rng = np.random.default_rng(1)
+    noisy = o.normalize(rng.standard_normal((16,) * 3) + 1j * rng.standard_normal((16,) * 3), p.dx, 3)
+    sim = m.SimulationObject(to_msm_params(p), n_streams=1)
+    sim.set_psi(0, noisy)
+    with pytest.raises(m.FourierAliasing):
+        sim.update()
+    assert sim.state(0).aliased == 1
+    ref = o.SimulationObject(p, noisy)
+    with pytest.raises(o.FourierAliasing) as oe:
+        ref.update()
+    assert abs(sim.state(0).alias_mass - oe.value.p_mass) <= 1e-10 * oe.value.p_mass
+    sim.close()
+
+
+def test_driver_runs_a_reference_toml(tmp_path):
+    """python -m msm_b200 --toml <file>: the host driver end to end, dumps in the reference layout."""
+    import shutil
+    from msm_b200 import driver
+    from msm_b200.config import read_toml
+    toml = tmp_path / "run.toml"
+    toml.write_text("""
+axis_length = 30
+final_sim_time = 1.0
+cfl = 0.5
+num_data_dumps = 5
+total_mass = 1e11
+hbar_ = 0.05
+sim_name = "spherical-tophat"
+k2_cutoff = 0.95
+alias_threshold = 0.02
+dims = 3
+size = 16
+[ics]
+type = "SphericalTophat"
+radius = 5.0
+slope = 50
+delta = 100
+[sampling]
+seeds = "1 to 3"
+scheme = "Husimi"
+""")
+    cfg = read_toml(str(toml))
+    res = driver.run(cfg, out_root=str(tmp_path / "sim-data"))
+    assert res["streams"] == 4 and res["stream_steps"] == 20
+    ot = o.read_toml(str(toml))
+    for p in o.simulation_iter(ot):
+        ref = o.run_stream(p, o.initial_wavefunction(p))
+        for idx, psi in ref.dumps:
+            d = tmp_path / "sim-data" / p.sim_name
+            got = np.load(open(d / f"psi_{idx:05d}_real", "rb"))[..., 0] + 1j * np.load(open(d / f"psi_{idx:05d}_imag", "rb"))[..., 0]
+            assert rel_l2(got, psi) < 1e-10, (p.sim_name, idx)
