@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,7 +26,7 @@
 #include "fft_pass.cuh"
 
 namespace msm {
-#define DECL(N) int launch_pass_##N(bool, int, int, const PassParams&, int, int, cudaStream_t);
+#define DECL(N) int launch_pass_##N(bool, int, int, bool, const PassParams&, int, int, cudaStream_t);
 DECL(2) DECL(4) DECL(8) DECL(16) DECL(32) DECL(64) DECL(128) DECL(256) DECL(512) DECL(1024)
 #undef DECL
 
@@ -36,6 +37,19 @@ pass_launcher_t get_pass_launcher(int n) {
 #undef C
     }
     return nullptr;
+}
+
+template <int N> static int radices_of(int r[4]) {
+    for (int i = 0; i < 4; ++i) r[i] = Plan<N>::R[i];
+    return Plan<N>::NS;
+}
+int plan_radices(int n, int r[4]) {
+    switch (n) {
+#define C(N) case N: return radices_of<N>(r);
+        C(2) C(4) C(8) C(16) C(32) C(64) C(128) C(256) C(512) C(1024)
+#undef C
+    }
+    return 0;
 }
 
 static int plan_T(int n) { return n >= 8 ? 8 : n; }
@@ -262,6 +276,7 @@ struct msm_ctx {
     std::vector<msm_profile_record> prof_rec;
     std::string err;
     pass_launcher_t launcher = nullptr;
+    bool xl = true;   // contiguous-axis thread mapping (MSM_B200_XL=0 selects the generic mapping, for A/B timing)
 };
 
 namespace {
@@ -439,7 +454,7 @@ int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2*
         int rc;
         {
             ProfScope ps(ctx, nm, pass_bytes(ctx, lop, sop, ns));
-            rc = ctx->launcher(inv, lop, sop, p, g.ntiles, groups, ctx->st);
+            rc = ctx->launcher(inv, lop, sop, axis == 0 && ctx->xl, p, g.ntiles, groups, ctx->st);
         }
         ctx->launches++;
         if (rc == -1) return fail(ctx, MSM_E_ARG, std::string("no kernel instance for ") + nm);
@@ -571,6 +586,7 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     ctx->C = 1;
     for (int d = 0; d < cfg->dims; ++d) ctx->C *= n;
     ctx->launcher = get_pass_launcher(n);
+    if (const char* e = getenv("MSM_B200_XL")) ctx->xl = atoi(e) != 0;
     int chunk = cfg->chunk_streams > 0 ? cfg->chunk_streams : 8;
     chunk = std::min(chunk, MAX_CHUNK);
     chunk = std::min(chunk, ctx->S + (ctx->S & 1));
@@ -632,11 +648,21 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     CUC(cudaMemsetAsync(ctx->alias_out, 0, sizeof(double) * ctx->S, ctx->st));
     CUC(cudaMemsetAsync(ctx->alias_partial, 0, sizeof(double) * (size_t)ctx->S * glast.ntiles, ctx->st));
     {
-        std::vector<double2> tw(n);
-        for (int j = 0; j < n; ++j) {
-            // exact at the octants, libm elsewhere
-            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
-            tw[j] = make_double2((double)cosl(a), (double)sinl(a));
+        // per-stage twiddle tables [k - 1][nu] = exp(-2 pi i k L nu / n)   (fft_pass.cuh: plan_tw_offset)
+        std::vector<double2> tw(n, make_double2(1.0, 0.0));
+        int rad[4];
+        const int nst = plan_radices(n, rad);
+        int off = 0, L = 1;
+        for (int q = 0; q + 1 < nst; ++q) {
+            const int M = n / (L * rad[q]);
+            for (int k = 1; k < rad[q]; ++k)
+                for (int nu = 0; nu < M; ++nu) {
+                    const long long j = (long long)k * L * nu;   // < n
+                    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+                    tw[off + (k - 1) * M + nu] = make_double2((double)cosl(a), (double)sinl(a));
+                }
+            off += (rad[q] - 1) * M;
+            L *= rad[q];
         }
         CUC(cudaMemcpyAsync(ctx->tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->st));
         CUC(cudaMemcpyAsync(ctx->ksq, ctx->h_ksq.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));

@@ -13,14 +13,14 @@ namespace msm {
 namespace {
 constexpr int N = MSM_FFT_N;
 
-template <bool INV, int LOP, int SOP>
+template <bool INV, int LOP, int SOP, bool XL>
 int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
     using PL = Plan<N>;
     static bool configured = false;
-    const size_t smem = PL::NS > 1 ? sizeof(double2) * N * PL::T : 0;
-    auto kern = fft_pass_kernel<N, INV, LOP, SOP>;
+    const size_t smem = pass_smem_bytes<N, LOP, SOP>();
+    auto kern = fft_pass_kernel<N, INV, LOP, SOP, XL>;
     if (!configured) {
-        if (smem > 48 * 1024) {
+        if (smem > 32 * 1024) {   // static __shared__ (reduction scratch) counts towards the 48 KiB default
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
@@ -33,10 +33,11 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
 }  // namespace
 
 // the (direction, load, store) combinations the step actually uses
-int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, const PassParams& p, int ntiles, int groups,
+int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, const PassParams& p, int ntiles, int groups,
                                      cudaStream_t st) {
-#define CASE(I, L, S) \
-    if (inv == I && lop == L && sop == S) return launch<I, L, S>(p, ntiles, groups, st);
+#define CASE(I, L, S)                                                                       \
+    if (inv == I && lop == L && sop == S)                                                   \
+        return xl ? launch<I, L, S, true>(p, ntiles, groups, st) : launch<I, L, S, false>(p, ntiles, groups, st);
     // inverse transforms
     CASE(true, L_NONE, S_NONE)
     CASE(true, L_NONE, S_SCALE)

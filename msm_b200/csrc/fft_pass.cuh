@@ -53,7 +53,7 @@ struct PassParams {
     long long outer_stride, inner_stride, lstride, astride;
     int lvalid;                           // valid lines per tile (1-D grids have a single line)
     // operators
-    const double2* twiddle;               // N entries  exp(-2 pi i j / N)
+    const double2* twiddle;               // per-stage tables, see plan_tw_offset
     const double2* dtab;                  // [n_streams][N]  per-axis drift factors (scale folded in), by stream id
     double kick[MAX_CHUNK];               // kappa per local index
     double2* pbuf;                        // pair buffers (rho / phi)
@@ -95,6 +95,18 @@ template <int N> constexpr int plan_L(int q) {   // product of radices of stages
     int l = 1;
     for (int i = 0; i < q; ++i) l *= Plan<N>::R[i];
     return l;
+}
+// Twiddles are stored per stage as [k - 1][nu] (nu fastest): entry = W_N^(k * L_q * nu), k = 1..r_q-1, nu < M_q.
+// Lanes that differ in nu then read consecutive 16-byte words and lanes that share nu broadcast, for both thread
+// mappings (a flat W_N^j table would make the contiguous-axis mapping gather with stride k).
+template <int N> constexpr int plan_tw_offset(int q) {
+    int off = 0, l = 1;
+    for (int i = 0; i < q; ++i) {
+        const int r = Plan<N>::R[i];
+        off += (r - 1) * (N / (l * r));
+        l *= r;
+    }
+    return off;
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -183,11 +195,22 @@ __device__ __forceinline__ double warp_max(double x) {
 //   outputs  position (kappa + L k) * M + nu                 (k = 0..r_q-1), twiddle W_N^(k L nu)
 // positions of stage 0 inputs are element indices of the line, positions of the last stage outputs are the
 // output indices (natural order).
-template <int N, bool INV, int Q>
+//
+// Two thread <-> data mappings (template flag XL):
+//   XL = false (strided axes)   tid = t * T + l, exchange buffer [position][line]
+//   XL = true  (contiguous axis) tid = l * NT + t, exchange buffer [line][position ^ swizzle]: a warp then reads 32
+//              consecutive elements of ONE line (512 contiguous bytes); the XOR of the low 3 position bits with bits
+//              3..5 keeps the stride-8 gather of the last stage conflict free.
+template <int N, bool XL> __device__ __forceinline__ int sm_index(int pos, int l) {
+    if (XL) return l * N + (pos ^ ((pos >> 3) & 7));
+    return pos * Plan<N>::T + l;
+}
+
+template <int N, bool INV, bool XL, int Q>
 __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm, int t, int l,
                                            const double2* __restrict__ tw) {
     using PL = Plan<N>;
-    constexpr int E = PL::E, T = PL::T, NT = PL::NT;
+    constexpr int E = PL::E, NT = PL::NT;
     constexpr int R = PL::R[Q];
     constexpr int L = plan_L<N>(Q);
     constexpr int M = N / (L * R);
@@ -204,11 +227,11 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
             for (int k = 0; k < R; ++k) {
                 double2 x = v[c * R + k];
                 if (k > 0) {
-                    double2 w = __ldg(&tw[k * L * nu]);
+                    double2 w = __ldg(&tw[plan_tw_offset<N>(Q) + (k - 1) * M + nu]);
                     if (INV) w.y = -w.y;
                     x = cmul(x, w);
                 }
-                sm[((kappa + L * k) * M + nu) * T + l] = x;
+                sm[sm_index<N, XL>((kappa + L * k) * M + nu, l)] = x;
             }
         }
         __syncthreads();
@@ -221,17 +244,25 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
             const int b = t + NT * c;
             const int kappa = b / M2, nu = b % M2;
 #pragma unroll
-            for (int n = 0; n < R2; ++n) v[c * R2 + n] = sm[(kappa * (M2 * R2) + n * M2 + nu) * T + l];
+            for (int n = 0; n < R2; ++n) v[c * R2 + n] = sm[sm_index<N, XL>(kappa * (M2 * R2) + n * M2 + nu, l)];
         }
         __syncthreads();
-        run_stages<N, INV, Q + 1>(v, sm, t, l, tw);
+        run_stages<N, INV, XL, Q + 1>(v, sm, t, l, tw);
     }
 }
 
-template <int N, bool INV, int LOP, int SOP>
+template <int LOP, int SOP> constexpr bool uses_stash() {
+    return LOP == L_KICK || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY;
+}
+template <int N, int LOP, int SOP> constexpr size_t pass_smem_bytes() {
+    return (Plan<N>::NS > 1 ? sizeof(double2) * N * Plan<N>::T : 0) +
+           (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * Plan<N>::THREADS : 0);
+}
+
+template <int N, bool INV, int LOP, int SOP, bool XL>
 __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kernel(const PassParams p) {
     using PL = Plan<N>;
-    constexpr int E = PL::E, T = PL::T, NT = PL::NT;
+    constexpr int E = PL::E, T = PL::T, NT = PL::NT, THREADS = PL::THREADS;
     constexpr int R0 = PL::R[0];
     constexpr int M0 = N / R0;
     constexpr int NB0 = E / R0;
@@ -240,17 +271,21 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     constexpr int NBL = E / RL;
 
     extern __shared__ double2 sm[];
-    __shared__ double red[32];
+    // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
+    // pair buffer is always accessed as full 16-byte words
+    double* stash = reinterpret_cast<double*>(sm + (PL::NS > 1 ? N * T : 0));
+    __shared__ double red[32], red2[32];
 
     const int tid = threadIdx.x;
-    const int l = tid % T, t = tid / T;
+    const int l = XL ? tid / NT : tid % T;
+    const int t = XL ? tid % NT : tid / T;
     const int tile = blockIdx.x;
     const bool lv = l < p.lvalid;
     const long long base = (long long)(tile / p.tiles_inner) * p.outer_stride +
                            (long long)(tile % p.tiles_inner) * p.inner_stride + (long long)l * p.lstride;
 
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
-    double kline = 0.0;   // partial k^2 sum in the reference's order (see k2_of)
+    double kline = 0.0;
     int c0 = 0, c1 = 0, c2 = 0;
     if constexpr (SOP == S_DRIFT_ALIAS || SOP == S_POISSON) {
         const int n = p.n;
@@ -283,13 +318,13 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
         const int li = g * p.gsz + q;
         if (li >= p.ns) break;
         const int s = p.sid[li];
+        const bool last_of_group = (q + 1 == p.gsz) || (li + 1 >= p.ns);
         const double2* __restrict__ src = p.src + (long long)(p.src_by_sid ? s : li) * p.src_sstride;
         double2* __restrict__ dst = p.dst + (long long)(p.dst_by_sid ? s : li) * p.dst_sstride;
         double2* __restrict__ pb = p.pbuf + (p.p_summed ? 0 : (long long)g * p.p_gstride);
-        const int comp = p.p_summed ? 0 : q;
 
         double2 v[E];
-        // ---- load (stage-0 input order) ----
+        // ---- load (stage-0 input order): all global loads first, operators afterwards ----
 #pragma unroll
         for (int c = 0; c < NB0; ++c) {
 #pragma unroll
@@ -298,26 +333,46 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                 const long long off = base + (long long)e * p.astride;
                 double2 x = make_double2(0.0, 0.0);
                 if (lv) x = src[off];
-                if constexpr (LOP == L_DRIFT) {
-                    const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
-                    x = cmul(x, w);
-                }
-                if constexpr (LOP == L_KICK) {
-                    // psi *= exp(-i kappa phi)    (simulation_object.rs:535-545)
-                    double ph = 0.0;
-                    if (lv) {
-                        const double* pd = reinterpret_cast<const double*>(pb + off);
-                        ph = pd[comp];
-                    }
-                    double sn, cs;
-                    sincos(-p.kick[li] * ph, &sn, &cs);
-                    x = cmul(x, make_double2(cs, sn));
-                }
                 v[c * R0 + n] = x;
             }
         }
+        if constexpr (LOP == L_DRIFT) {
+#pragma unroll
+            for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    const int e = n * M0 + t + NT * c;
+                    const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
+                    v[c * R0 + n] = cmul(v[c * R0 + n], w);
+                }
+            }
+        }
+        if constexpr (LOP == L_KICK) {
+            // psi *= exp(-i kappa phi)    (simulation_object.rs:535-545); phi_a + i phi_b is read once per pair
+#pragma unroll
+            for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    const int e = n * M0 + t + NT * c;
+                    const long long off = base + (long long)e * p.astride;
+                    double ph;
+                    double* slot = &stash[(c * R0 + n) * THREADS + tid];
+                    if (q == 0) {
+                        double2 pp = make_double2(0.0, 0.0);
+                        if (lv) pp = pb[off];
+                        ph = pp.x;
+                        if (!last_of_group) *slot = p.p_summed ? pp.x : pp.y;
+                    } else {
+                        ph = *slot;
+                    }
+                    double sn, cs;
+                    sincos(-p.kick[li] * ph, &sn, &cs);
+                    v[c * R0 + n] = cmul(v[c * R0 + n], make_double2(cs, sn));
+                }
+            }
+        }
 
-        run_stages<N, INV, 0>(v, sm, t, l, p.twiddle);
+        run_stages<N, INV, XL, 0>(v, sm, t, l, p.twiddle);
 
         // ---- store (last-stage output order) ----
         double acc = 0.0, acc2 = 0.0;
@@ -354,15 +409,15 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                 if constexpr (SOP == S_RHO_KEEP || SOP == S_RHO_ONLY) {
                     // rho = A real(psi conj(psi))   (simulation_object.rs:1051-1062)
                     const double rho = p.rho_coef * (x.x * x.x + x.y * x.y);
-                    if (lv) {
-                        double* pd = reinterpret_cast<double*>(pb + off);
-                        if (p.p_summed) {
-                            pd[0] = (p.rho_accumulate || q > 0) ? pd[0] + rho : rho;
-                            if (!(p.rho_accumulate || q > 0)) pd[1] = 0.0;
-                        } else {
-                            pd[comp] = rho;
-                            if (q == 0 && li + 1 >= p.ns) pd[1] = 0.0;   // odd stream count: empty partner
-                        }
+                    double* slot = &stash[(c * RL + k) * THREADS + tid];
+                    if (!p.p_summed) {
+                        // pair buffer rho_a + i rho_b: the first stream parks its value, the second writes both
+                        if (!last_of_group) *slot = rho;
+                        else if (lv) pb[off] = (q == 0) ? make_double2(rho, 0.0) : make_double2(*slot, rho);
+                    } else {
+                        const double sum = (q == 0) ? rho : *slot + rho;
+                        if (!last_of_group) *slot = sum;
+                        else if (lv) pb[off] = make_double2(p.rho_accumulate ? pb[off].x + sum : sum, 0.0);
                     }
                 }
                 if constexpr (SOP != S_RHO_ONLY && SOP != S_MAX) {
@@ -377,7 +432,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
             __syncthreads();
             if (tid == 0) {
                 double tot = 0.0;
-                for (int w = 0; w < (PL::THREADS + 31) / 32; ++w) tot += red[w];
+                for (int w = 0; w < (THREADS + 31) / 32; ++w) tot += red[w];
                 p.alias_partial[(long long)s * p.ntiles + tile] = tot;
             }
             __syncthreads();
@@ -386,17 +441,31 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
             acc = warp_max(acc);
             acc2 = warp_max(acc2);
             if ((tid & 31) == 0) {
-                atomicMax(&p.maxbits[2 * li], (unsigned long long)__double_as_longlong(acc));
-                atomicMax(&p.maxbits[2 * li + 1], (unsigned long long)__double_as_longlong(acc2));
+                red[tid >> 5] = acc;
+                red2[tid >> 5] = acc2;
             }
+            __syncthreads();
+            if (tid == 0) {
+                double m1 = 0.0, m2 = 0.0;
+                for (int w = 0; w < (THREADS + 31) / 32; ++w) {
+                    m1 = fmax(m1, red[w]);
+                    m2 = fmax(m2, red2[w]);
+                }
+                // bit patterns of non-negative doubles order like unsigned integers
+                if (m1 > 0.0) atomicMax(&p.maxbits[2 * li], (unsigned long long)__double_as_longlong(m1));
+                if (m2 > 0.0) atomicMax(&p.maxbits[2 * li + 1], (unsigned long long)__double_as_longlong(m2));
+            }
+            __syncthreads();
         }
     }
 }
 
 // host-side launcher, one translation unit per N (fft_inst.cu compiled with -DMSM_FFT_N=<N>)
-typedef int (*pass_launcher_t)(bool inv, int lop, int sop, const PassParams& p, int ntiles, int groups,
+typedef int (*pass_launcher_t)(bool inv, int lop, int sop, bool xl, const PassParams& p, int ntiles, int groups,
                                cudaStream_t st);
 pass_launcher_t get_pass_launcher(int n);
+// radices of the plan for length n (host side, for building the twiddle tables); returns the number of stages
+int plan_radices(int n, int radices[4]);
 const char* pass_kernel_name(int n, bool inv, int lop, int sop);
 
 }  // namespace msm

@@ -49,18 +49,18 @@ def test_step_properties_at_full_size(size):
     dv = p.dx ** 3
     psik0 = ctx.get_psik(0)
     n0 = np.vdot(psik0, psik0).real * dv
-    assert abs(n0 - 1.0) < 1e-6                         # normalised IC + tiny noise
+    assert abs(n0 - 1.0) < 2e-2                         # normalised IC + Wigner noise (cells / (2 n_tot) of extra norm)
     # zero-dt step is the identity on psi_k
     ctx.step(np.zeros(2), np.zeros(2))
     assert rel_l2(ctx.get_psik(0), psik0) < 1e-14
-    # a real step: norm conserved (every operator is unitary), alias mass ~ 0 for a smooth field
+    # a real step: norm conserved (every operator is unitary), alias mass tiny for a smooth field + noise
     pm = ctx.potential_max()
     dt = p.cfl * np.pi * p.hbar_ / pm                   # simulation_object.rs:906-909
     alias = ctx.step(dt * p.hbar_ / 4.0, dt / p.hbar_)
     k1 = ctx.get_psik(0)
     assert abs(np.vdot(k1, k1).real * dv - n0) < 1e-12
     assert rel_l2(k1, psik0) > 1e-6                     # it did move
-    assert alias[0] < 1e-12 and alias[1] < 1e-12
+    assert alias[0] < 1e-5 and alias[1] < 1e-5          # only the white Wigner noise reaches beyond the cutoff
     # exact time reversal of the split step: D(-dt/2) K(-dt) D(-dt/2) undoes D(dt/2) K(dt) D(dt/2)
     ctx.step(-dt * p.hbar_ / 4.0, -dt / p.hbar_)
     assert rel_l2(ctx.get_psik(0), psik0) < 1e-12
