@@ -236,7 +236,7 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    fft = [r for r in prof if r["name"].startswith("fft_pass")]
+    fft = [r for r in prof if r["name"].startswith("fft_")]
     top = max(fft, key=lambda r: r["ms_total"])
     ach = top["algorithmic_bytes"] / (top["ms_total"] * 1e-3) / 1e9
     kernel_ms = sum(r["ms_total"] for r in prof)

@@ -26,7 +26,7 @@
 #include "fft_pass.cuh"
 
 namespace msm {
-#define DECL(N) int launch_pass_##N(bool, int, int, bool, const PassParams&, int, int, cudaStream_t);
+#define DECL(N) int launch_pass_##N(bool, int, int, bool, bool, const PassParams&, int, int, cudaStream_t);
 DECL(2) DECL(4) DECL(8) DECL(16) DECL(32) DECL(64) DECL(128) DECL(256) DECL(512) DECL(1024)
 #undef DECL
 
@@ -55,34 +55,60 @@ int plan_radices(int n, int r[4]) {
 static int plan_T(int n) { return n >= 8 ? 8 : n; }
 
 // ---------------------------------------------------------------------------------------------------------
-// small kernels
+// device layout
 // ---------------------------------------------------------------------------------------------------------
+// Host buffers are linear: cell (i, j, k) at q = (i*n + j)*n + k (the reference's layout).  On the device 3-D grids
+// with n >= 512 block the slowest axis: i = (i_hi, i_lo) with LO = 2^lb values of i_lo, rows of n contiguous k stay
+// intact and are ordered [i_hi][j][i_lo].  A z-line then touches n/LO pages of 2 MiB instead of n (512^3: 32 vs
+// 512 -- the linear layout thrashes the TLB in the z pass: 3.8 TB/s vs 5.4 TB/s for the y pass, profiles/README.md),
+// and a y-line 2*LO pages.  lb == 0 is the identity.
+__host__ __device__ __forceinline__ long long blk_index(long long q, int n, int lb) {
+    if (lb == 0) return q;
+    const long long k = q % n, r = q / n;
+    const long long j = r % n, i = r / n;
+    return (((((i >> lb) * n + j) << lb) + (i & ((1 << lb) - 1))) * n) + k;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels (all iterate over the LINEAR cell index q; the device side of every access goes through blk_index)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_relayout(const double2* __restrict__ in, double2* __restrict__ out, long long cells, int n, int lb,
+                           int to_device) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x) {
+        const long long b = blk_index(q, n, lb);
+        if (to_device) out[b] = in[q];
+        else out[q] = in[b];
+    }
+}
 __global__ void k_interleave(const double* __restrict__ re, const double* __restrict__ im, double2* __restrict__ out,
-                             long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = make_double2(re[i], im[i]);
+                             long long cells, int n, int lb) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x)
+        out[blk_index(i, n, lb)] = make_double2(re[i], im[i]);
 }
 __global__ void k_deinterleave(const double2* __restrict__ in, double* __restrict__ re, double* __restrict__ im,
-                               long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+                               long long cells, int n, int lb) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells;
          i += (long long)gridDim.x * blockDim.x) {
-        double2 v = in[i];
+        double2 v = in[blk_index(i, n, lb)];
         re[i] = v.x;
         im[i] = v.y;
     }
 }
-__global__ void k_extract(const double2* __restrict__ in, double* __restrict__ out, long long n, int comp) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+__global__ void k_extract(const double2* __restrict__ in, double* __restrict__ out, long long cells, int n, int lb,
+                          int comp) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells;
          i += (long long)gridDim.x * blockDim.x) {
-        double2 v = in[i];
+        double2 v = in[blk_index(i, n, lb)];
         out[i] = comp ? v.y : v.x;
     }
 }
 // alias_out[s] = dv * sum_tiles partial[s][tile]    (fixed summation order: deterministic)
-__global__ void k_alias_reduce(const double* __restrict__ partial, double* __restrict__ out, int ntiles, double dv) {
+__global__ void k_alias_reduce(const double* __restrict__ partial, double* __restrict__ out, int ntiles, int pitch,
+                               double dv) {
     __shared__ double sh[256];
     const int s = blockIdx.x;
-    const double* p = partial + (long long)s * ntiles;
+    const double* p = partial + (long long)s * pitch;
+    (void)pitch;
     double a = 0.0;
     for (int i = threadIdx.x; i < ntiles; i += blockDim.x) a += p[i];
     sh[threadIdx.x] = a;
@@ -120,7 +146,8 @@ __global__ void k_scale_real(double2* __restrict__ a, long long n, double f) {
 
 // ---- on-device initial conditions (restates simulator/src/ics.rs) --------------------------
 // psi(i,j,k) = gx[k] * gy[j] * gz[i] * norm          (cold_gauss, ics.rs:24-162: separable, already normalised)
-__global__ void k_ic_separable(double2* __restrict__ psi, const double* __restrict__ g, int n, int dims, double norm) {
+__global__ void k_ic_separable(double2* __restrict__ psi, const double* __restrict__ g, int n, int dims, double norm,
+                               int lb) {
     long long total = 1;
     for (int d = 0; d < dims; ++d) total *= n;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
@@ -131,12 +158,12 @@ __global__ void k_ic_separable(double2* __restrict__ psi, const double* __restri
         double v = g[c0];
         if (dims >= 2) v = g[n + c1] * v;
         if (dims >= 3) v = g[2 * n + c2] * v;
-        psi[q] = make_double2(v * norm, 0.0);
+        psi[blk_index(q, n, lb)] = make_double2(v * norm, 0.0);
     }
 }
 // spherical_tophat (ics.rs:165-280): sqrt(1 + delta / (1 + exp(slope (r/R - 1)))), un-normalised
 __global__ void k_ic_tophat(double2* __restrict__ psi, int n, int dims, double dx, double half, double radius,
-                            double delta, double slope) {
+                            double delta, double slope, int lb) {
     long long total = 1;
     for (int d = 0; d < dims; ++d) total *= n;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
@@ -153,7 +180,7 @@ __global__ void k_ic_tophat(double2* __restrict__ psi, int n, int dims, double d
         else if (dims == 2) r = sqrt(b * b + a * a + 0.0);
         else r = sqrt(a * a + 0.0 + 0.0);
         double ramp = 1.0 / (1.0 + exp(slope * (r / radius - 1.0)));
-        psi[q] = make_double2(sqrt(1.0 + delta * ramp), 0.0);
+        psi[blk_index(q, n, lb)] = make_double2(sqrt(1.0 + delta * ramp), 0.0);
     }
 }
 __global__ void k_norm2_partial(const double2* __restrict__ a, long long n, double* __restrict__ partial) {
@@ -188,18 +215,20 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
 }
 // sample_quantum_perturbation, Wigner / Husimi (ics.rs:560-646): psi = (psi sqrt(dV) + (N + iN) / div) / sqrt(dV)
-__global__ void k_sample_gauss(double2* __restrict__ psi, long long n, uint64_t seed, double sqrt_dv, double div) {
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+__global__ void k_sample_gauss(double2* __restrict__ psi, long long cells, uint64_t seed, double sqrt_dv, double div,
+                               int n, int lb) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x) {
         uint32_t c0 = (uint32_t)q, c1 = (uint32_t)((uint64_t)q >> 32), c2 = 0u, c3 = 0u;
         philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
         const double u1 = u53(c0, c1), u2 = u53(c2, c3);
         const double r = sqrt(-2.0 * log(u1));
         double sn, cs;
         sincos(2.0 * 3.14159265358979323846 * u2, &sn, &cs);
-        double2 v = psi[q];
+        const long long b = blk_index(q, n, lb);   // the Philox counter is the LINEAR cell index
+        double2 v = psi[b];
         v.x = (v.x * sqrt_dv + (r * cs) / div) / sqrt_dv;
         v.y = (v.y * sqrt_dv + (r * sn) / div) / sqrt_dv;
-        psi[q] = v;
+        psi[b] = v;
     }
 }
 }  // namespace msm
@@ -250,6 +279,7 @@ struct ProfEvent {
 struct msm_ctx {
     msm_config cfg;
     int n = 0, dims = 0, S = 0, chunk = 0, T = 0;
+    int lb = 0;   // log2 of the slow-axis block (device layout, see blk_index)
     long long C = 0;
     cudaStream_t st = nullptr;
     double2 *X = nullptr, *Tscr = nullptr, *P = nullptr, *tw = nullptr, *dtab = nullptr;
@@ -264,7 +294,7 @@ struct msm_ctx {
     std::vector<char> in_k, has_psi;
     std::vector<double> h_ksq;
     double four_pi2 = 0, k2_max = 0, dv = 0;
-    int ntiles_last = 0;
+    int ntiles_last = 0, ntiles_used = 0;   // allocation pitch bound / tiles of the last forward pass as launched
     uint64_t bytes = 0, launches = 0;
     void* comm = nullptr;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;
@@ -277,6 +307,9 @@ struct msm_ctx {
     std::string err;
     pass_launcher_t launcher = nullptr;
     bool xl = true;   // contiguous-axis thread mapping (MSM_B200_XL=0 selects the generic mapping, for A/B timing)
+    bool pipe = false; // persistent cp.async-pipelined kernel for N >= 128 (MSM_B200_PIPE=1; slower so far)
+    int tiles_per_cta = 4;   // consecutive tiles per CTA of the one-tile kernel; next item is prefetched into L2
+    int num_sms = 148;
 };
 
 namespace {
@@ -293,12 +326,12 @@ int fail(msm_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 struct Geom {
-    int axis, tiles_inner, ntiles, lvalid;
-    long long outer, inner, lstride, astride;
+    int axis, tiles_inner, ntiles, lvalid, olb = 0, alb = 0;
+    long long outer, inner, lstride, astride, outer_lo = 0, astride_lo = 0;
 };
-Geom make_geom(const msm_ctx* c, int axis) {
+Geom make_geom(const msm_ctx* c, int axis, int T) {
     Geom g{};
-    const int n = c->n, T = c->T;
+    const int n = c->n;
     g.axis = axis;
     if (axis == 0) {
         const long long nlines = c->C / n;
@@ -310,20 +343,28 @@ Geom make_geom(const msm_ctx* c, int axis) {
         g.astride = 1;
         g.lvalid = (int)std::min<long long>(T, nlines);
     } else if (axis == 1) {
+        // along j for fixed (i, k0..k0+T-1): tile = i * (n/T) + m
+        const long long LO = 1LL << c->lb;
         g.tiles_inner = n / T;
         g.ntiles = g.tiles_inner * (c->dims == 3 ? n : 1);
         g.inner = T;
-        g.outer = (long long)n * n;
+        g.olb = c->lb;                       // i = (i_hi, i_lo)
+        g.outer = (long long)n * n * LO;     // i_hi
+        g.outer_lo = n;                      // i_lo
         g.lstride = 1;
-        g.astride = n;
+        g.astride = (long long)n * LO;       // j
         g.lvalid = T;
     } else {
+        // along i for fixed (j, k0..k0+T-1): tile = j * (n/T) + m
+        const long long LO = 1LL << c->lb;
+        g.tiles_inner = n / T;
         g.ntiles = (int)(((long long)n * n) / T);
-        g.tiles_inner = g.ntiles;
         g.inner = T;
-        g.outer = 0;
+        g.outer = (long long)n * LO;         // j
         g.lstride = 1;
-        g.astride = (long long)n * n;
+        g.alb = c->lb;
+        g.astride = (long long)n * n * LO;   // i_hi
+        g.astride_lo = n;                    // i_lo
         g.lvalid = T;
     }
     return g;
@@ -433,7 +474,8 @@ int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2*
     const int groups = (ns + o.gsz - 1) / o.gsz;
     for (int k = 0; k < ctx->dims; ++k) {
         const int axis = inv ? ctx->dims - 1 - k : k;
-        const Geom g = make_geom(ctx, axis);
+        const bool pipe = ctx->pipe && ctx->n >= PIPE_MIN_N;
+        const Geom g = make_geom(ctx, axis, pipe ? PIPE_T : ctx->T);
         const bool first = (k == 0), last = (k == ctx->dims - 1);
         const int lop = (first && o.lop_first != L_NONE) ? o.lop_first : o.lop_each;
         const int sop = last ? o.sop_last : o.sop_each;
@@ -447,14 +489,22 @@ int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2*
         p.inner_stride = g.inner;
         p.lstride = g.lstride;
         p.astride = g.astride;
+        p.olb = g.olb;
+        p.alb = g.alb;
+        p.row_lb = ctx->lb;
+        p.outer_lo = g.outer_lo;
+        p.astride_lo = g.astride_lo;
         p.lvalid = g.lvalid;
         p.ntiles = g.ntiles;
         char nm[96];
-        snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s>", ctx->n, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop));
+        p.grid_ctas = ctx->num_sms;
+        p.tiles_per_cta = pipe ? 1 : ctx->tiles_per_cta;
+        snprintf(nm, sizeof nm, "%s<%d,%s,%s,%s,%s>", pipe ? "fft_pipe" : "fft_pass", ctx->n, inv ? "inv" : "fwd",
+                 lop_name(lop), sop_name(sop), axis == 0 ? "x" : axis == 1 ? "y" : "z");
         int rc;
         {
             ProfScope ps(ctx, nm, pass_bytes(ctx, lop, sop, ns));
-            rc = ctx->launcher(inv, lop, sop, axis == 0 && ctx->xl, p, g.ntiles, groups, ctx->st);
+            rc = ctx->launcher(inv, lop, sop, axis == 0 && ctx->xl, pipe, p, g.ntiles, groups, ctx->st);
         }
         ctx->launches++;
         if (rc == -1) return fail(ctx, MSM_E_ARG, std::string("no kernel instance for ") + nm);
@@ -587,6 +637,11 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     for (int d = 0; d < cfg->dims; ++d) ctx->C *= n;
     ctx->launcher = get_pass_launcher(n);
     if (const char* e = getenv("MSM_B200_XL")) ctx->xl = atoi(e) != 0;
+    if (const char* e = getenv("MSM_B200_PIPE")) ctx->pipe = atoi(e) != 0;
+    if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
+    ctx->lb = (cfg->dims == 3 && n >= 512) ? 4 : 0;
+    if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;
+    ctx->num_sms = prop.multiProcessorCount;
     int chunk = cfg->chunk_streams > 0 ? cfg->chunk_streams : 8;
     chunk = std::min(chunk, MAX_CHUNK);
     chunk = std::min(chunk, ctx->S + (ctx->S & 1));
@@ -635,8 +690,9 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     CUC(cudaMalloc(&ctx->tw, sizeof(double2) * n));
     CUC(cudaMalloc(&ctx->dtab, sizeof(double2) * n * ctx->S));
     CUC(cudaMalloc(&ctx->ksq, sizeof(double) * n));
-    const Geom glast = make_geom(ctx, ctx->dims - 1);
+    const Geom glast = make_geom(ctx, ctx->dims - 1, std::min(ctx->T, PIPE_T));   // finest tiling any kernel uses
     ctx->ntiles_last = glast.ntiles;
+    ctx->ntiles_used = make_geom(ctx, ctx->dims - 1, (ctx->pipe && n >= PIPE_MIN_N) ? PIPE_T : ctx->T).ntiles;
     CUC(cudaMalloc(&ctx->alias_partial, sizeof(double) * (size_t)ctx->S * glast.ntiles));
     CUC(cudaMalloc(&ctx->alias_out, sizeof(double) * ctx->S));
     CUC(cudaMalloc(&ctx->maxbits, sizeof(unsigned long long) * (ctx->S + 2)));
@@ -722,7 +778,14 @@ int msm_synchronize(msm_ctx* ctx) {
 int msm_set_psi(msm_ctx* ctx, int32_t s, const double* psi) {
     if (!ctx || !psi || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_set_psi: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
-    CU(cudaMemcpyAsync(ctx->X + (size_t)s * ctx->C, psi, sizeof(double2) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->lb == 0) {
+        CU(cudaMemcpyAsync(ctx->X + (size_t)s * ctx->C, psi, sizeof(double2) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
+    } else {   // host layout is linear, device layout blocked: stage through scratch slot 0
+        CU(cudaMemcpyAsync(ctx->Tscr, psi, sizeof(double2) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
+        k_relayout<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->Tscr, ctx->X + (size_t)s * ctx->C, ctx->C, ctx->n, ctx->lb, 1);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(ctx->st));
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
@@ -735,7 +798,7 @@ int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* 
     double* stage = reinterpret_cast<double*>(ctx->Tscr);   // 2*C doubles = one scratch slot
     CU(cudaMemcpyAsync(stage, re, sizeof(double) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(stage + ctx->C, im, sizeof(double) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
-    k_interleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(stage, stage + ctx->C, ctx->X + (size_t)s * ctx->C, ctx->C);
+    k_interleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(stage, stage + ctx->C, ctx->X + (size_t)s * ctx->C, ctx->C, ctx->n, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->st));
@@ -769,6 +832,12 @@ int msm_get_psi_interleaved(msm_ctx* ctx, int32_t s, double* out) {
     const double2* d = nullptr;
     int rc = psi_on_device(ctx, s, &d);
     if (rc) return rc;
+    if (ctx->lb != 0) {   // back to the host's linear layout through the (idle) pair buffer
+        k_relayout<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, ctx->P, ctx->C, ctx->n, ctx->lb, 0);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        d = ctx->P;
+    }
     CU(cudaMemcpyAsync(out, d, sizeof(double2) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return MSM_OK;
@@ -781,7 +850,7 @@ int msm_get_psi(msm_ctx* ctx, int32_t s, double* re, double* im) {
     int rc = psi_on_device(ctx, s, &d);
     if (rc) return rc;
     double* planes = reinterpret_cast<double*>(ctx->P);   // 2*C doubles
-    k_deinterleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, planes, planes + ctx->C, ctx->C);
+    k_deinterleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, planes, planes + ctx->C, ctx->C, ctx->n, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());
     if (re) CU(cudaMemcpyAsync(re, planes, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
@@ -795,7 +864,14 @@ int msm_get_psik_interleaved(msm_ctx* ctx, int32_t s, double* out) {
     CU(cudaSetDevice(ctx->cfg.device));
     int rc = ensure_kspace(ctx, std::vector<int>{s});
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out, ctx->X + (size_t)s * ctx->C, sizeof(double2) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    const double2* d = ctx->X + (size_t)s * ctx->C;
+    if (ctx->lb != 0) {
+        k_relayout<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, ctx->Tscr, ctx->C, ctx->n, ctx->lb, 0);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        d = ctx->Tscr;
+    }
+    CU(cudaMemcpyAsync(out, d, sizeof(double2) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return MSM_OK;
 }
@@ -874,7 +950,7 @@ int msm_get_potential(msm_ctx* ctx, int32_t s, double* phi) {
     rc = poisson(ctx, 1, false, nullptr);
     if (rc) return rc;
     double* stage = reinterpret_cast<double*>(ctx->Tscr);
-    k_extract<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->P, stage, ctx->C, 0);
+    k_extract<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->P, stage, ctx->C, ctx->n, ctx->lb, 0);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(phi, stage, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
@@ -958,7 +1034,7 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
     }
     {
         ProfScope ps(ctx, "alias_reduce", 8.0 * ctx->S * ctx->ntiles_last);
-        k_alias_reduce<<<ctx->S, 256, 0, ctx->st>>>(ctx->alias_partial, ctx->alias_out, ctx->ntiles_last, ctx->dv);
+        k_alias_reduce<<<ctx->S, 256, 0, ctx->st>>>(ctx->alias_partial, ctx->alias_out, ctx->ntiles_used, ctx->ntiles_used, ctx->dv);
     }
     ctx->launches++;
     CU(cudaGetLastError());
@@ -989,7 +1065,10 @@ int msm_fft(int32_t device, int32_t dims, int32_t size, int32_t inverse, int32_t
         return code;
     };
     const size_t cb = sizeof(double2) * (size_t)ctx->C;
-    if (cudaMemcpyAsync(ctx->X, data, cb * batch, cudaMemcpyHostToDevice, ctx->st) != cudaSuccess) return done(MSM_E_CUDA);
+    for (int b = 0; b < batch; ++b) {
+        rc = msm_set_psi(ctx, b, data + 2 * (size_t)ctx->C * b);   // linear host layout -> device layout
+        if (rc) return done(rc);
+    }
     std::vector<int> ids(batch);
     for (int i = 0; i < batch; ++i) ids[i] = i;
     for (int i = 0; i < batch; i += ctx->chunk) {
@@ -1000,7 +1079,15 @@ int msm_fft(int32_t device, int32_t dims, int32_t size, int32_t inverse, int32_t
         rc = run_transform(ctx, inverse != 0, &ids[i], ns, ctx->X, 1, ctx->X, 1, o);
         if (rc) return done(rc);
     }
-    if (cudaMemcpyAsync(data, ctx->X, cb * batch, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return done(MSM_E_CUDA);
+    for (int b = 0; b < batch; ++b) {
+        const double2* d = ctx->X + (size_t)b * ctx->C;
+        if (ctx->lb != 0) {
+            k_relayout<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, ctx->Tscr, ctx->C, ctx->n, ctx->lb, 0);
+            d = ctx->Tscr;
+        }
+        if (cudaMemcpyAsync(data + 2 * (size_t)ctx->C * b, d, cb, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return done(MSM_E_CUDA);
+        if (cudaStreamSynchronize(ctx->st) != cudaSuccess) return done(MSM_E_CUDA);
+    }
     if (cudaStreamSynchronize(ctx->st) != cudaSuccess) {
         ctx->err = cudaGetErrorString(cudaGetLastError());
         return done(MSM_E_CUDA);
@@ -1070,7 +1157,7 @@ int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double*
     if (3 * n > 4096) return fail(ctx, MSM_E_ARG, "size too large for the IC staging buffer");
     CU(cudaMemcpyAsync(ctx->scratch_small, g.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
     double2* psi = ctx->X + (size_t)s * ctx->C;
-    k_ic_separable<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->scratch_small, n, d, 1.0);
+    k_ic_separable<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->scratch_small, n, d, 1.0, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->st));
@@ -1086,7 +1173,7 @@ int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t s, double axis_length, double 
     CU(cudaSetDevice(ctx->cfg.device));
     double2* psi = ctx->X + (size_t)s * ctx->C;
     const double dx = axis_length / (double)ctx->n;   // ics.rs:203 (axis length, not the comoving box)
-    k_ic_tophat<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->n, ctx->dims, dx, axis_length / 2.0, radius, delta, slope);
+    k_ic_tophat<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->n, ctx->dims, dx, axis_length / 2.0, radius, delta, slope, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());
     int rc = normalize_on_device(ctx, psi);   // ics.rs:261
@@ -1118,7 +1205,7 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     CU(cudaSetDevice(ctx->cfg.device));
     const double sqrt_dv = sqrt(pow(ctx->cfg.dx, (double)ctx->dims));
     const double div = sqrt(n_tot) * (scheme == MSM_SCHEME_WIGNER ? 2.0 : sqrt(2.0));   // ics.rs:581 / :625
-    k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div);
+    k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div, ctx->n, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());
     return MSM_OK;

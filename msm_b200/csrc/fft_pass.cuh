@@ -45,12 +45,16 @@ struct PassParams {
     int src_by_sid, dst_by_sid;           // slot = stream id (resident array) or local index (scratch)
     int ns, gsz;                          // streams in this launch, streams per CTA group
     int sid[MAX_CHUNK];
-    // tile geometry:  offset(tile, l, e) = (tile / tiles_inner) * outer_stride + (tile % tiles_inner) * inner_stride
-    //                                      + l * lstride + e * astride
+    // tile geometry:  offset(tile, l, e) = outer(tile / tiles_inner) + (tile % tiles_inner) * inner_stride
+    //                                      + l * lstride + along(e)
+    //   outer(o) = (o >> olb) * outer_stride + (o & lomask) * outer_lo ;  along(e) likewise with alb / astride(_lo)
     int axis;                             // 0 = contiguous (x), 1 = stride n (y), 2 = stride n^2 (z)
     int n;
     int tiles_inner;
     long long outer_stride, inner_stride, lstride, astride;
+    // blocked slow axis: index o / e splits into (hi, lo) with lo = low `olb` / `alb` bits
+    int olb, alb, row_lb;
+    long long outer_lo, astride_lo;
     int lvalid;                           // valid lines per tile (1-D grids have a single line)
     // operators
     const double2* twiddle;               // per-stage tables, see plan_tw_offset
@@ -65,6 +69,8 @@ struct PassParams {
     double* alias_partial;                // [n_streams][ntiles] by stream id
     int ntiles;
     unsigned long long* maxbits;          // [2 * buffers]: bit patterns of non-negative doubles
+    int grid_ctas;                        // persistent (pipelined) kernel: CTAs to launch = SM count
+    int tiles_per_cta;                    // one-tile kernel: consecutive tiles walked by one CTA (L2 prefetch depth)
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -120,6 +126,47 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 // multiply by -i (forward) or +i (inverse)
 template <bool INV> __device__ __forceinline__ double2 rot90(double2 a) {
     return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+// 1 / x for normal positive x: hardware seed + two Newton steps (<= 1 ulp; the full IEEE division costs ~3x more)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+static __device__ __noinline__ void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }
+
+// sin and cos of the kick phase -kappa*phi.  |x| <= 1e5: three-term Cody-Waite reduction by pi/2 (exact products via
+// FMA) + the fdlibm minimax kernels on [-pi/4, pi/4] (< 1 ulp); larger arguments take the library path.
+__device__ __forceinline__ void kick_sincos(double x, double* s, double* c) {
+    if (fabs(x) > 1.0e5) {
+        sincos_slow(x, s, c);
+        return;
+    }
+    const double q = rint(x * 0.6366197723675814);
+    double r = fma(-q, 1.5707963267948966, x);
+    r = fma(-q, 6.123233995736766e-17, r);
+    r = fma(-q, -1.4973849048591698e-33, r);
+    const int n = (int)q;
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double a = (n & 1) ? cs : sn, b = (n & 1) ? sn : cs;
+    *s = (n & 2) ? -a : a;
+    *c = ((n + 1) & 2) ? -b : b;
 }
 
 template <int R, bool INV> struct Dft;
@@ -274,15 +321,41 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
     double* stash = reinterpret_cast<double*>(sm + (PL::NS > 1 ? N * T : 0));
-    __shared__ double red[32], red2[32];
+    __shared__ double red[2][32], red2[32];
+    double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
+    int item_parity = 0;
 
     const int tid = threadIdx.x;
     const int l = XL ? tid / NT : tid % T;
     const int t = XL ? tid % NT : tid / T;
-    const int tile = blockIdx.x;
     const bool lv = l < p.lvalid;
-    const long long base = (long long)(tile / p.tiles_inner) * p.outer_stride +
-                           (long long)(tile % p.tiles_inner) * p.inner_stride + (long long)l * p.lstride;
+    const int g = blockIdx.y;
+
+    // L2 prefetch of one tile: the CTA's 512 threads cover the tile's 128-byte lines (strided axes: one line per
+    // position e; contiguous axis: the tile is T * N * 16 contiguous bytes).
+    auto tile_origin = [&](int tile_) -> long long {
+        const int o = tile_ / p.tiles_inner;
+        return (long long)(o >> p.olb) * p.outer_stride + (long long)(o & ((1 << p.olb) - 1)) * p.outer_lo +
+               (long long)(tile_ % p.tiles_inner) * p.inner_stride;
+    };
+    auto along = [&](int e) -> long long {
+        return (long long)(e >> p.alb) * p.astride + (long long)(e & ((1 << p.alb) - 1)) * p.astride_lo;
+    };
+    auto prefetch_tile = [&](const double2* arr, int tile_) {
+        const long long o = tile_origin(tile_);
+        if (XL) {
+            for (int j = tid; j < (N * T) / 8; j += THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(arr + o + (long long)j * 8));
+        } else {
+            for (int e = tid; e < N; e += THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(arr + o + along(e)));
+        }
+    };
+
+    for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
+    const int tile = blockIdx.x * p.tiles_per_cta + ti;
+    if (tile >= p.ntiles) break;
+    const long long base = tile_origin(tile) + (long long)l * p.lstride;
 
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
     double kline = 0.0;
@@ -290,9 +363,9 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     if constexpr (SOP == S_DRIFT_ALIAS || SOP == S_POISSON) {
         const int n = p.n;
         if (p.axis == 0) {
-            const int line = tile * T + l;
-            c1 = line % n;
-            c2 = line / n;
+            const int line = tile * T + l;   // row index in the (blocked) device layout, see core.cu blk_index
+            c1 = (line >> p.row_lb) % n;
+            c2 = ((line >> p.row_lb) / n << p.row_lb) + (line & ((1 << p.row_lb) - 1));
         } else if (p.axis == 1) {
             c2 = tile / p.tiles_inner;
             c0 = (tile % p.tiles_inner) * T + l;
@@ -313,7 +386,6 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
         return s * p.four_pi2;
     };
 
-    const int g = blockIdx.y;
     for (int q = 0; q < p.gsz; ++q) {
         const int li = g * p.gsz + q;
         if (li >= p.ns) break;
@@ -323,6 +395,19 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
         double2* __restrict__ dst = p.dst + (long long)(p.dst_by_sid ? s : li) * p.dst_sstride;
         double2* __restrict__ pb = p.pbuf + (p.p_summed ? 0 : (long long)g * p.p_gstride);
 
+        // pull the NEXT item (partner stream of this tile, else first stream of the next tile) into L2 now, so its
+        // loads find the data on chip: DRAM stays busy while this item computes
+        if (p.tiles_per_cta > 1 || p.gsz > 1) {
+            const bool same_tile = !last_of_group;
+            const int ntile = same_tile ? tile : tile + 1;
+            const int nli = same_tile ? li + 1 : g * p.gsz;
+            if (ntile < p.ntiles && (same_tile || ti + 1 < p.tiles_per_cta)) {
+                const int ns_ = p.sid[nli];
+                prefetch_tile(p.src + (long long)(p.src_by_sid ? ns_ : nli) * p.src_sstride, ntile);
+                if (LOP == L_KICK && !same_tile) prefetch_tile(pb, ntile);
+            }
+        }
+
         double2 v[E];
         // ---- load (stage-0 input order): all global loads first, operators afterwards ----
 #pragma unroll
@@ -330,7 +415,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
 #pragma unroll
             for (int n = 0; n < R0; ++n) {
                 const int e = n * M0 + t + NT * c;
-                const long long off = base + (long long)e * p.astride;
+                const long long off = base + along(e);
                 double2 x = make_double2(0.0, 0.0);
                 if (lv) x = src[off];
                 v[c * R0 + n] = x;
@@ -354,7 +439,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
 #pragma unroll
                 for (int n = 0; n < R0; ++n) {
                     const int e = n * M0 + t + NT * c;
-                    const long long off = base + (long long)e * p.astride;
+                    const long long off = base + along(e);
                     double ph;
                     double* slot = &stash[(c * R0 + n) * THREADS + tid];
                     if (q == 0) {
@@ -366,7 +451,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                         ph = *slot;
                     }
                     double sn, cs;
-                    sincos(-p.kick[li] * ph, &sn, &cs);
+                    kick_sincos(-p.kick[li] * ph, &sn, &cs);
                     v[c * R0 + n] = cmul(v[c * R0 + n], make_double2(cs, sn));
                 }
             }
@@ -381,7 +466,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
 #pragma unroll
             for (int k = 0; k < RL; ++k) {
                 const int e = t + NT * c + LL * k;
-                const long long off = base + (long long)e * p.astride;
+                const long long off = base + along(e);
                 double2 x = v[c * RL + k];
                 if constexpr (SOP == S_SCALE) {
                     x.x *= p.scale;
@@ -398,7 +483,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                 if constexpr (SOP == S_POISSON) {
                     // phi_k = c rho_k / k^2, 0/0 at k = 0 replaced by 0  (simulation_object.rs:1076-1102)
                     const double k2 = k2_of(e);
-                    const double m = (k2 == 0.0) ? 0.0 : p.poisson_coef / k2;
+                    const double m = (k2 == 0.0) ? 0.0 : p.poisson_coef * fast_rcp(k2);
                     x.x *= m;
                     x.y *= m;
                 }
@@ -427,42 +512,60 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
         }
 
         if constexpr (SOP == S_DRIFT_ALIAS) {
+            // one partial per (stream, tile), summed in a fixed order -> deterministic.  `red` is double buffered by
+            // item parity: by the time a parity is reused the stage barriers of the item in between have passed.
             acc = warp_sum(acc);
-            if ((tid & 31) == 0) red[tid >> 5] = acc;
+            if ((tid & 31) == 0) red[item_parity][tid >> 5] = acc;
             __syncthreads();
             if (tid == 0) {
                 double tot = 0.0;
-                for (int w = 0; w < (THREADS + 31) / 32; ++w) tot += red[w];
+                for (int w = 0; w < (THREADS + 31) / 32; ++w) tot += red[item_parity][w];
                 p.alias_partial[(long long)s * p.ntiles + tile] = tot;
             }
-            __syncthreads();
+            item_parity ^= 1;
         }
         if constexpr (SOP == S_MAX) {
-            acc = warp_max(acc);
-            acc2 = warp_max(acc2);
+            run_max = fmax(run_max, acc);
+            run_max2 = fmax(run_max2, acc2);
+            if (p.gsz > 1) {   // several buffers per CTA: flush per item (not used by the solver, kept for generality)
+                const double m1 = warp_max(run_max), m2 = warp_max(run_max2);
+                if ((tid & 31) == 0) {
+                    if (m1 > 0.0) atomicMax(&p.maxbits[2 * li], (unsigned long long)__double_as_longlong(m1));
+                    if (m2 > 0.0) atomicMax(&p.maxbits[2 * li + 1], (unsigned long long)__double_as_longlong(m2));
+                }
+                run_max = run_max2 = 0.0;
+            }
+        }
+    }
+    }   // tiles of this CTA
+
+    if constexpr (SOP == S_MAX) {
+        if (p.gsz == 1 && g < p.ns) {
+            // max|re|, max|im| of this CTA's tiles of buffer g; bit patterns of non-negative doubles order like integers
+            const double m1 = warp_max(run_max), m2 = warp_max(run_max2);
             if ((tid & 31) == 0) {
-                red[tid >> 5] = acc;
-                red2[tid >> 5] = acc2;
+                red[0][tid >> 5] = m1;
+                red2[tid >> 5] = m2;
             }
             __syncthreads();
             if (tid == 0) {
-                double m1 = 0.0, m2 = 0.0;
+                double a = 0.0, b = 0.0;
                 for (int w = 0; w < (THREADS + 31) / 32; ++w) {
-                    m1 = fmax(m1, red[w]);
-                    m2 = fmax(m2, red2[w]);
+                    a = fmax(a, red[0][w]);
+                    b = fmax(b, red2[w]);
                 }
-                // bit patterns of non-negative doubles order like unsigned integers
-                if (m1 > 0.0) atomicMax(&p.maxbits[2 * li], (unsigned long long)__double_as_longlong(m1));
-                if (m2 > 0.0) atomicMax(&p.maxbits[2 * li + 1], (unsigned long long)__double_as_longlong(m2));
+                if (a > 0.0) atomicMax(&p.maxbits[2 * g], (unsigned long long)__double_as_longlong(a));
+                if (b > 0.0) atomicMax(&p.maxbits[2 * g + 1], (unsigned long long)__double_as_longlong(b));
             }
-            __syncthreads();
         }
     }
 }
 
 // host-side launcher, one translation unit per N (fft_inst.cu compiled with -DMSM_FFT_N=<N>)
-typedef int (*pass_launcher_t)(bool inv, int lop, int sop, bool xl, const PassParams& p, int ntiles, int groups,
-                               cudaStream_t st);
+typedef int (*pass_launcher_t)(bool inv, int lop, int sop, bool xl, bool pipe, const PassParams& p, int ntiles,
+                               int groups, cudaStream_t st);
+constexpr int PIPE_MIN_N = 128;   // the pipelined kernel (fft_pipe.cuh) exists for N >= 128
+constexpr int PIPE_T = 4;         // lines per tile of the pipelined kernel
 pass_launcher_t get_pass_launcher(int n);
 // radices of the plan for length n (host side, for building the twiddle tables); returns the number of stages
 int plan_radices(int n, int radices[4]);

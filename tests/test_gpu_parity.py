@@ -418,3 +418,36 @@ scheme = "Husimi"
             d = tmp_path / "sim-data" / p.sim_name
             got = np.load(open(d / f"psi_{idx:05d}_real", "rb"))[..., 0] + 1j * np.load(open(d / f"psi_{idx:05d}_imag", "rb"))[..., 0]
             assert rel_l2(got, psi) < 1e-10, (p.sim_name, idx)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device layout: the blocked slow axis (used for n >= 512) forced on small grids, where the oracle is cheap
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lb,size", [(2, 16), (3, 32), (1, 64), (4, 16)])
+def test_blocked_device_layout_on_small_grids(monkeypatch, lb, size):
+    monkeypatch.setenv("MSM_B200_LB", str(lb))
+    rng = np.random.default_rng(size + lb)
+    a = rng.standard_normal((3, size, size, size)) + 1j * rng.standard_normal((3, size, size, size))
+    assert rel_l2(m.forward(a, 3), sf.fftn(a, axes=(1, 2, 3), norm="ortho")) < 1e-13
+    ps = oracle_streams("spherical-tophat", size, limit=3)
+    sim, refs, worst = run_both(ps, 4)
+    assert worst < 1e-10
+    # on-device ICs and the sampler address cells through the same mapping
+    p = ps[0]
+    ctx = make_ctx(p, 1)
+    ctx.ic_spherical_tophat(0, p.axis_length, 5.0, 100.0, 50.0)
+    ctx.sample_perturbation(0, "Wigner", 5, p.n_tot)
+    want = o.sample_quantum_perturbation(o.spherical_tophat(p, 5.0, 100.0, 50.0), p, {"seed": 5, "scheme": "Wigner"})
+    assert rel_l2(ctx.get_psi(0), want) < 1e-13
+    assert rel_l2(ctx.get_potential(0), _oracle_potential(p, want)) < 1e-12
+    re, im = ctx.get_psi_planes(0)
+    assert rel_l2(re + 1j * im, want) < 1e-13
+    assert rel_l2(ctx.get_psik(0), o.forward(want)) < 1e-13
+    ctx.close()
+    sim.close()
+
+
+def _oracle_potential(p, psi):
+    s = o.SimulationObject(p, psi)
+    s.calculate_potential()
+    return s.phi.real
