@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsm_b200.so")
+LIB_PATH = os.environ.get("MSM_B200_LIB", os.path.join(_HERE, "libmsm_b200.so"))   # override: A/B builds only
 
 MSM_OK = 0
 MSM_E_ARG, MSM_E_CUDA, MSM_E_NCCL, MSM_E_ALIASING, MSM_E_NAN, MSM_E_STATE, MSM_E_NOMEM, MSM_E_IO = \

@@ -308,6 +308,7 @@ struct msm_ctx {
     pass_launcher_t launcher = nullptr;
     bool xl = true;   // contiguous-axis thread mapping (MSM_B200_XL=0 selects the generic mapping, for A/B timing)
     bool pipe = false; // persistent cp.async-pipelined kernel for N >= 128 (MSM_B200_PIPE=1; slower so far)
+    bool fuse = true;  // fused passes (MSM_B200_FUSE=0 runs the plain 3+3 pass sequences, for A/B timing)
     int tiles_per_cta = 4;   // consecutive tiles per CTA of the one-tile kernel; next item is prefetched into L2
     int num_sms = 148;
 };
@@ -381,6 +382,7 @@ const char* sop_name(int s) {
         case S_RHO_ONLY: return "rho";
         case S_POISSON: return "poisson";
         case S_MAX: return "max";
+        case S_POISSON_INV: return "poisson+inv";
     }
     return "?";
 }
@@ -447,9 +449,15 @@ struct XformOps {
     unsigned long long* maxbits = nullptr;
 };
 
-// d-dimensional transform of the streams ids[0..ns): first pass reads `src`, every pass writes `work`.
-int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2* src, int src_by_sid, double2* work,
-                  int work_by_sid, const XformOps& o) {
+struct PassSpec {
+    int axis;
+    bool inv;
+    int lop, sop;
+};
+
+// a sequence of axis passes over the streams ids[0..ns): the first pass reads `src`, every pass writes `work`.
+int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, int ns, const double2* src, int src_by_sid,
+               double2* work, int work_by_sid, const XformOps& o) {
     PassParams p{};
     p.src_sstride = p.dst_sstride = ctx->C;
     p.ns = ns;
@@ -472,13 +480,12 @@ int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2*
     p.alias_partial = ctx->alias_partial;
     p.maxbits = o.maxbits ? o.maxbits : ctx->maxbits;
     const int groups = (ns + o.gsz - 1) / o.gsz;
-    for (int k = 0; k < ctx->dims; ++k) {
-        const int axis = inv ? ctx->dims - 1 - k : k;
+    for (size_t k = 0; k < seq.size(); ++k) {
+        const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop;
+        const bool inv = seq[k].inv;
         const bool pipe = ctx->pipe && ctx->n >= PIPE_MIN_N;
         const Geom g = make_geom(ctx, axis, pipe ? PIPE_T : ctx->T);
-        const bool first = (k == 0), last = (k == ctx->dims - 1);
-        const int lop = (first && o.lop_first != L_NONE) ? o.lop_first : o.lop_each;
-        const int sop = last ? o.sop_last : o.sop_each;
+        const bool first = (k == 0);
         p.src = first ? src : work;
         p.src_by_sid = first ? src_by_sid : work_by_sid;
         p.dst = work;
@@ -511,6 +518,22 @@ int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2*
         if (rc != 0) return fail(ctx, MSM_E_CUDA, std::string(nm) + ": " + cudaGetErrorString((cudaError_t)rc));
     }
     return MSM_OK;
+}
+
+// d-dimensional transform (forward x,y,z / inverse z,y,x) with the operators of `o`
+int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2* src, int src_by_sid, double2* work,
+                  int work_by_sid, const XformOps& o) {
+    std::vector<PassSpec> seq;
+    for (int k = 0; k < ctx->dims; ++k) {
+        const bool first = (k == 0), last = (k == ctx->dims - 1);
+        PassSpec s;
+        s.axis = inv ? ctx->dims - 1 - k : k;
+        s.inv = inv;
+        s.lop = (first && o.lop_first != L_NONE) ? o.lop_first : o.lop_each;
+        s.sop = last ? o.sop_last : o.sop_each;
+        seq.push_back(s);
+    }
+    return run_passes(ctx, seq, ids, ns, src, src_by_sid, work, work_by_sid, o);
 }
 
 int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
@@ -550,20 +573,26 @@ int allreduce_rho(msm_ctx* ctx) {
 }
 
 // Poisson solve in place on `nbuf` pair buffers starting at ctx->P:  phi = F^-1[ c/(k^2 n^d) F[rho] ]
+// dims >= 2: the last forward pass, the multiply and the first inverse pass run as ONE kernel (S_POISSON_INV).
 int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits) {
     std::vector<int> ids(nbuf);
     for (int i = 0; i < nbuf; ++i) ids[i] = i;
-    XformOps f;
-    f.gsz = 1;
-    f.sop_last = S_POISSON;
-    f.poisson_coef = ctx->cfg.poisson_coeff / pow((double)ctx->n, (double)ctx->dims);
-    int rc = run_transform(ctx, false, ids.data(), nbuf, ctx->P, 0, ctx->P, 0, f);
-    if (rc) return rc;
-    XformOps b;
-    b.gsz = 1;
-    b.sop_last = max_only ? S_MAX : S_NONE;
-    b.maxbits = maxbits;
-    return run_transform(ctx, true, ids.data(), nbuf, ctx->P, 0, ctx->P, 0, b);
+    XformOps o;
+    o.gsz = 1;
+    o.poisson_coef = ctx->cfg.poisson_coeff / pow((double)ctx->n, (double)ctx->dims);
+    o.maxbits = maxbits;
+    const int d = ctx->dims;
+    const bool fuse = d >= 2 && ctx->fuse && !(ctx->pipe && ctx->n >= PIPE_MIN_N);
+    std::vector<PassSpec> seq;
+    for (int a = 0; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_NONE});
+    if (fuse) {
+        seq.push_back(PassSpec{d - 1, false, L_NONE, S_POISSON_INV});
+    } else {
+        seq.push_back(PassSpec{d - 1, false, L_NONE, S_POISSON});
+        seq.push_back(PassSpec{d - 1, true, L_NONE, d == 1 ? (max_only ? S_MAX : S_NONE) : S_NONE});
+    }
+    for (int a = d - 2; a >= 0; --a) seq.push_back(PassSpec{a, true, L_NONE, (a == 0 && max_only) ? S_MAX : S_NONE});
+    return run_passes(ctx, seq, ids.data(), nbuf, ctx->P, 0, ctx->P, 0, o);
 }
 
 }  // namespace
@@ -638,6 +667,7 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     ctx->launcher = get_pass_launcher(n);
     if (const char* e = getenv("MSM_B200_XL")) ctx->xl = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_PIPE")) ctx->pipe = atoi(e) != 0;
+    if (const char* e = getenv("MSM_B200_FUSE")) ctx->fuse = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
     ctx->lb = (cfg->dims == 3 && n >= 512) ? 4 : 0;
     if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;

@@ -74,6 +74,7 @@ int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, bool p
     CASE(false, L_NONE, S_DRIFT)
     CASE(false, L_NONE, S_DRIFT_ALIAS)
     CASE(false, L_NONE, S_POISSON)
+    CASE(false, L_NONE, S_POISSON_INV)
     CASE(false, L_KICK, S_DRIFT)
     CASE(false, L_KICK, S_DRIFT_ALIAS)
 #undef CASE

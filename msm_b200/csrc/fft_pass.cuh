@@ -35,7 +35,10 @@ enum StoreOp {
     S_RHO_KEEP = 4,     // store psi and rho = rho_coef |psi|^2    (last inverse pass of the drift transform)
     S_RHO_ONLY = 5,     // rho only, psi is not written            (potential at time t: only max|phi| is needed)
     S_POISSON = 6,      // * poisson_coef / k^2, DC -> 0           (last forward pass of the Poisson solve)
-    S_MAX = 7           // no store, max|re| and max|im|           (last inverse pass of the dt Poisson solve)
+    S_MAX = 7,          // no store, max|re| and max|im|           (last inverse pass of the dt Poisson solve)
+    S_POISSON_INV = 8   // S_POISSON, then the INVERSE transform of the same lines, then store: the last forward
+                        // and first inverse pass of the Poisson solve share their tile, so the k-space potential
+                        // never travels to HBM
 };
 
 struct PassParams {
@@ -71,6 +74,7 @@ struct PassParams {
     unsigned long long* maxbits;          // [2 * buffers]: bit patterns of non-negative doubles
     int grid_ctas;                        // persistent (pipelined) kernel: CTAs to launch = SM count
     int tiles_per_cta;                    // one-tile kernel: consecutive tiles walked by one CTA (L2 prefetch depth)
+    int zero;                             // always 0; only the compiler does not know (see data_dependent)
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -93,6 +97,7 @@ MSM_PLAN(32,   8, 8,  1, 2, 4, 8, 1, 1)
 MSM_PLAN(64,   8, 8,  1, 2, 8, 8, 1, 1)
 MSM_PLAN(128,  8, 8,  1, 3, 2, 8, 8, 1)
 MSM_PLAN(256,  8, 8,  2, 3, 4, 8, 8, 1)
+// 512: E = 8 / 2 CTAs per SM measured best (E = 16: -3 %, E = 32 with 3 CTAs: -27 %; profiles/README.md)
 MSM_PLAN(512,  8, 8,  2, 3, 8, 8, 8, 1)
 MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #undef MSM_PLAN
@@ -167,6 +172,13 @@ __device__ __forceinline__ void kick_sincos(double x, double* s, double* c) {
     const double a = (n & 1) ? cs : sn, b = (n & 1) ? sn : cs;
     *s = (n & 2) ? -a : a;
     *c = ((n + 1) & 2) ? -b : b;
+}
+
+// ptr + (bits(x) & zero): the same pointer, but every load through it is data dependent on x for the assembler's
+// scheduler as well.  Used to stop it from fetching the (loop-invariant, L1-resident) twiddles of a whole item ahead of
+// the tile data and parking them in local memory when registers are capped at 64.
+__device__ __forceinline__ const double2* data_dependent(const double2* ptr, double x, int zero) {
+    return ptr + (__double2loint(x) & zero);
 }
 
 template <int R, bool INV> struct Dft;
@@ -299,7 +311,7 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
 }
 
 template <int LOP, int SOP> constexpr bool uses_stash() {
-    return LOP == L_KICK || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY;
+    return LOP == L_KICK || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY || SOP == S_POISSON_INV;
 }
 template <int N, int LOP, int SOP> constexpr size_t pass_smem_bytes() {
     return (Plan<N>::NS > 1 ? sizeof(double2) * N * Plan<N>::T : 0) +
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
     double kline = 0.0;
     int c0 = 0, c1 = 0, c2 = 0;
-    if constexpr (SOP == S_DRIFT_ALIAS || SOP == S_POISSON) {
+    if constexpr (SOP == S_DRIFT_ALIAS || SOP == S_POISSON || SOP == S_POISSON_INV) {
         const int n = p.n;
         if (p.axis == 0) {
             const int line = tile * T + l;   // row index in the (blocked) device layout, see core.cu blk_index
@@ -385,6 +397,18 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
         else s = kline + p.ksq[e];
         return s * p.four_pi2;
     };
+
+    if constexpr (SOP == S_POISSON_INV) {
+        // c / (k^2 n^d) of this thread's 8 outputs, once per tile and while registers are free; parked in the stash
+#pragma unroll
+        for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+            for (int k = 0; k < RL; ++k) {
+                const double k2 = k2_of(t + NT * c + LL * k);
+                stash[(c * RL + k) * THREADS + tid] = (k2 == 0.0) ? 0.0 : p.poisson_coef * fast_rcp(k2);
+            }
+        }
+    }
 
     for (int q = 0; q < p.gsz; ++q) {
         const int li = g * p.gsz + q;
@@ -457,7 +481,40 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
             }
         }
 
-        run_stages<N, INV, XL, 0>(v, sm, t, l, p.twiddle);
+        const double2* tw1 = data_dependent(p.twiddle, v[0].x, p.zero);
+        run_stages<N, INV, XL, 0>(v, sm, t, l, tw1);
+
+        if constexpr (SOP == S_POISSON_INV) {
+            // phi_k = c rho_k / k^2 (DC -> 0) on the forward outputs, which each thread holds at e = t + NT * m:
+            // exactly the element set the inverse transform's first stage wants, in a different register order
+#pragma unroll
+            for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+                for (int k = 0; k < RL; ++k) {
+                    const double m = stash[(c * RL + k) * THREADS + tid];
+                    v[c * RL + k].x *= m;
+                    v[c * RL + k].y *= m;
+                }
+            }
+            const double2* tw2 = data_dependent(p.twiddle, v[0].x, p.zero);   // v[0] is the multiplied value here
+            if constexpr (R0 == E && RL == E) {
+                run_stages<N, !INV, XL, 0>(v, sm, t, l, tw2);   // register orders coincide (e.g. 512 = 8*8*8)
+            } else {
+                double2 w[E];
+#pragma unroll
+                for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                    for (int n = 0; n < R0; ++n) {
+                        constexpr int PER = E / RL;           // output slot of element index m: (m % PER) * RL + m / PER
+                        const int m = n * (E / R0) + c;
+                        w[c * R0 + n] = v[(m % PER) * RL + m / PER];
+                    }
+                }
+                run_stages<N, !INV, XL, 0>(w, sm, t, l, tw2);
+#pragma unroll
+                for (int j = 0; j < E; ++j) v[j] = w[j];
+            }
+        }
 
         // ---- store (last-stage output order) ----
         double acc = 0.0, acc2 = 0.0;
