@@ -25,7 +25,12 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-ALG_BYTES_PER_CELL_UPDATE = 480.0       # DESIGN.md section 4 (independent streams)
+ALG_BYTES_PER_CELL_UPDATE = 480.0       # DESIGN.md section 3 (independent streams, 3-pass transforms)
+
+
+def alg_bytes(coupling, s_local):
+    """algorithmic HBM bytes per cell-update of the 3-pass model: 480 independent, 296 + 368/S_local summed"""
+    return 480.0 if coupling == "independent" else 296.0 + 368.0 / s_local
 
 
 def parse():
@@ -40,6 +45,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--coupling", default="independent", choices=["independent", "summed"],
+                    help="independent = the reference's semantics (headline); summed = north-star variant with one "
+                         "ncclAllReduce of the density per potential")
     return ap.parse_args()
 
 
@@ -191,12 +199,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    coupling = m.COUPLING_SUMMED if args.coupling == "summed" else m.COUPLING_INDEPENDENT
+
+    def comm_kwargs():
+        """a fresh ncclUniqueId per context (rank 0 creates, torch.distributed broadcasts); summed mode only"""
+        if coupling != m.COUPLING_SUMMED or world == 1:
+            return {}
+        import ctypes as C
+        from msm_b200._lib import lib
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            assert lib.msm_nccl_unique_id(buf) == 0
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        return dict(rank=rank, nranks=world, n_streams_global=n_total, nccl_unique_id=bytes(uid.cpu().numpy().tobytes()))
+
     # ---- resident run: streams generated on the device, timed with CUDA events on the library's stream ----------
     sim = None
     note = ""
     for chunk in (args.chunk, 4, 2):
         try:
-            sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk)
+            sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=coupling,
+                                     **comm_kwargs())
             break
         except m.MsmError as e:
             if e.code != -7:
@@ -243,9 +268,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": top["ms_total"] / top["launches"], "share_of_step": top["ms_total"] / kernel_ms,
-                "step": {"algorithmic_bytes_per_cell_update": ALG_BYTES_PER_CELL_UPDATE,
-                         "achieved": value * ALG_BYTES_PER_CELL_UPDATE / 1e9, "frac": value * ALG_BYTES_PER_CELL_UPDATE / 1e9 / peak,
-                         "frac_of_8TBps": value * ALG_BYTES_PER_CELL_UPDATE / 8e12},
+                "step": {"algorithmic_bytes_per_cell_update": alg_bytes(args.coupling, n_local),
+                         "achieved_per_gpu": value / world * alg_bytes(args.coupling, n_local) / 1e9,
+                         "frac": value / world * alg_bytes(args.coupling, n_local) / 1e9 / peak,
+                         "frac_of_8TBps": value / world * alg_bytes(args.coupling, n_local) / 8e12},
                 "kernels": [{"name": r["name"], "launches": r["launches"], "ms": round(r["ms_total"], 3),
                              "GBps": round(r["algorithmic_bytes"] / (r["ms_total"] * 1e-3) / 1e9, 1)}
                             for r in sorted(prof, key=lambda r: -r["ms_total"])]}
@@ -259,7 +285,8 @@ def main():
         hnp, renp, imnp = host.numpy(), out_re.numpy(), out_im.numpy()
         hnp[:] = g.get_psi(0).reshape(-1).view(np.float64)        # a realistic wavefunction as the host-side IC
         sim.close()
-        sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk)
+        sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=coupling,
+                                 **comm_kwargs())
         g = sim.grid
         import ctypes as C
         from msm_b200._lib import lib, check
@@ -300,7 +327,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"synthetic {size}^3 x {n_total} streams fp64 static box (BASELINE configs[4])",
-                           "streams_per_gpu": n_local, "coupling": "independent", "chunk_streams": chunk,
+                           "streams_per_gpu": n_local, "coupling": args.coupling, "chunk_streams": chunk,
                            "l2": "inputs larger than L2 (2 GiB per stream vs 126 MB)",
                            "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}

@@ -760,7 +760,10 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
         nccl_uid_t id;
         memcpy(&id, cfg->nccl_unique_id, 128);
         int rc = g_nccl.CommInitRank(&ctx->comm, cfg->nranks, id, cfg->rank);
-        if (rc != 0) return bail(MSM_E_NCCL, "ncclCommInitRank failed");
+        if (rc != 0)
+            return bail(MSM_E_NCCL, std::string("ncclCommInitRank failed: ") +
+                                        (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?") + " (code " +
+                                        std::to_string(rc) + ")");
     }
 #undef CUC
     *out = ctx;

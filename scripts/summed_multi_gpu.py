@@ -1,0 +1,59 @@
+"""Coupled (summed-density) mode across ranks: torchrun --nproc-per-node R scripts/summed_multi_gpu.py
+Each rank owns S/R streams; the density is ncclAllReduce'd inside libmsm_b200 (communicator from a unique id that
+rank 0 creates and torch.distributed broadcasts); every rank checks its streams against the CPU oracle ensemble."""
+import ctypes as C
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import msm_b200 as m
+from msm_b200._lib import lib
+from oracle import msm_oracle as o
+import golden_util as gu
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def fresh_unique_id():
+    """a ncclUniqueId can initialise ONE communicator: rank 0 makes one per context, torch.distributed broadcasts it"""
+    uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        assert lib.msm_nccl_unique_id(buf) == 0
+        uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    return bytes(uid.cpu().numpy().tobytes())
+
+
+for name, per_rank, size in (("spherical-tophat", 3, None), ("spherical-tophat-cosmo", 2, None), ("spherical-tophat", 2, 64)):
+    S = per_rank * world
+    ps = gu.oracle_streams(name, size, limit=S)
+    psi0s = [gu.initial_wavefunction(p) for p in ps]
+    ens = o.SummedEnsemble(ps[0], psi0s)
+    uid_bytes = fresh_unique_id()
+    sim = m.SimulationObject(gu.to_msm_params(ps[0]), n_streams=per_rank, coupling=m.COUPLING_SUMMED, device=local,
+                             rank=rank, nranks=world, n_streams_global=S, nccl_unique_id=uid_bytes)
+    mine = list(range(rank * per_rank, (rank + 1) * per_rank))
+    for li, s in enumerate(mine):
+        sim.set_psi(li, psi0s[s])
+    for _ in range(4):
+        sim.update()
+        ens.update()
+    worst = 0.0
+    for li, s in enumerate(mine):
+        got = sim.get_psi(li)
+        worst = max(worst, np.linalg.norm((got - ens.streams[s].psi).ravel()) / np.linalg.norm(ens.streams[s].psi.ravel()))
+    st = sim.state(0)
+    ok = worst < 1e-10 and abs(st.dt - ens.head.last_dt) <= 1e-12 * ens.head.last_dt
+    print(f"rank {rank} {name} size {size or 16} S={S}: psi rel-L2 {worst:.2e}, dt {st.dt:.6e} vs {ens.head.last_dt:.6e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    sim.close()
+    t = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+    dist.all_reduce(t)
+    if int(t.item()) != 0:
+        dist.destroy_process_group()
+        sys.exit(1)
+dist.destroy_process_group()
