@@ -292,6 +292,11 @@ struct msm_ctx {
     unsigned long long* maxbits = nullptr;
     double* scratch_small = nullptr;  // 4096 doubles
     std::vector<char> in_k, has_psi;
+    // max|phi| of the CURRENT psi_k, computed eagerly at the end of msm_step (its first pass is fused into the step's
+    // last pass); msm_potential_max returns it without touching the GPU while it is valid
+    std::vector<char> pmax_valid;
+    std::vector<double> pmax_cache;
+    std::vector<int> pmax_pending;   // streams whose value still sits in `maxbits` (position = index in this list)
     std::vector<double> h_ksq;
     double four_pi2 = 0, k2_max = 0, dv = 0;
     int ntiles_last = 0, ntiles_used = 0;   // allocation pitch bound / tiles of the last forward pass as launched
@@ -371,7 +376,7 @@ Geom make_geom(const msm_ctx* c, int axis, int T) {
     return g;
 }
 
-const char* lop_name(int l) { return l == L_NONE ? "none" : l == L_DRIFT ? "drift" : "kick"; }
+const char* lop_name(int l) { return l == L_NONE ? "none" : l == L_DRIFT ? "drift" : l == L_KICK ? "kick" : "invx+kick"; }
 const char* sop_name(int s) {
     switch (s) {
         case S_NONE: return "none";
@@ -383,15 +388,19 @@ const char* sop_name(int s) {
         case S_POISSON: return "poisson";
         case S_MAX: return "max";
         case S_POISSON_INV: return "poisson+inv";
+        case S_RHO_KEEP_FX: return "psi+rho+fwdx";
+        case S_RHO_ONLY_FX: return "rho+fwdx";
+        case S_DRIFT_ALIAS_IZ: return "drift+alias+inv";
     }
     return "?";
 }
 
 double pass_bytes(const msm_ctx* c, int lop, int sop, int ns) {
     double per = 16.0;                                   // read the line
-    if (lop == L_KICK) per += 8.0;                       // phi
-    if (sop != S_RHO_ONLY && sop != S_MAX) per += 16.0;  // write the line
-    if (sop == S_RHO_KEEP || sop == S_RHO_ONLY) per += 8.0;
+    if (lop == L_KICK || lop == L_KICK_IX) per += 8.0;   // phi (16 B per pair of streams)
+    if (sop != S_RHO_ONLY && sop != S_RHO_ONLY_FX && sop != S_MAX) per += 16.0;   // write the line
+    if (sop_is_rho(sop)) per += 8.0;                     // rho (16 B per pair)
+    if (sop == S_DRIFT_ALIAS_IZ) per += 16.0;            // second output
     return per * (double)c->C * ns;
 }
 
@@ -447,6 +456,7 @@ struct XformOps {
     const double* kick = nullptr;   // per local index
     double2* pbuf = nullptr;
     unsigned long long* maxbits = nullptr;
+    double2* dst2 = nullptr;
 };
 
 struct PassSpec {
@@ -479,6 +489,7 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
     p.scale = o.scale;
     p.alias_partial = ctx->alias_partial;
     p.maxbits = o.maxbits ? o.maxbits : ctx->maxbits;
+    p.dst2 = o.dst2;
     const int groups = (ns + o.gsz - 1) / o.gsz;
     for (size_t k = 0; k < seq.size(); ++k) {
         const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop;
@@ -574,7 +585,10 @@ int allreduce_rho(msm_ctx* ctx) {
 
 // Poisson solve in place on `nbuf` pair buffers starting at ctx->P:  phi = F^-1[ c/(k^2 n^d) F[rho] ]
 // dims >= 2: the last forward pass, the multiply and the first inverse pass run as ONE kernel (S_POISSON_INV).
-int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits) {
+// x_fwd_done: the buffers already hold rho after the forward x pass (S_RHO_*_FX); x_inv_skip: leave out the inverse x
+// pass (the kick kernel L_KICK_IX runs it on the fly).
+int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits, bool x_fwd_done = false,
+            bool x_inv_skip = false) {
     std::vector<int> ids(nbuf);
     for (int i = 0; i < nbuf; ++i) ids[i] = i;
     XformOps o;
@@ -584,15 +598,51 @@ int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits) 
     const int d = ctx->dims;
     const bool fuse = d >= 2 && ctx->fuse && !(ctx->pipe && ctx->n >= PIPE_MIN_N);
     std::vector<PassSpec> seq;
-    for (int a = 0; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_NONE});
+    for (int a = x_fwd_done ? 1 : 0; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_NONE});
     if (fuse) {
         seq.push_back(PassSpec{d - 1, false, L_NONE, S_POISSON_INV});
     } else {
         seq.push_back(PassSpec{d - 1, false, L_NONE, S_POISSON});
         seq.push_back(PassSpec{d - 1, true, L_NONE, d == 1 ? (max_only ? S_MAX : S_NONE) : S_NONE});
     }
-    for (int a = d - 2; a >= 0; --a) seq.push_back(PassSpec{a, true, L_NONE, (a == 0 && max_only) ? S_MAX : S_NONE});
+    for (int a = d - 2; a >= (x_inv_skip ? 1 : 0); --a)
+        seq.push_back(PassSpec{a, true, L_NONE, (a == 0 && max_only) ? S_MAX : S_NONE});
     return run_passes(ctx, seq, ids.data(), nbuf, ctx->P, 0, ctx->P, 0, o);
+}
+
+bool full_fusion(const msm_ctx* ctx) {
+    return ctx->fuse && ctx->dims >= 2 && ctx->cfg.coupling == MSM_COUPLING_INDEPENDENT &&
+           !(ctx->pipe && ctx->n >= PIPE_MIN_N);
+}
+
+// dt-potential of a chunk whose psi_k has ALREADY been taken through the inverse pass of the last axis into the
+// scratch slots: remaining inverse passes -> rho (+ forward x) -> Poisson -> max|phi| into maxbits[pos...]
+int dt_potential_tail(msm_ctx* ctx, const int* ids, int ns, unsigned long long* maxbits) {
+    const int d = ctx->dims;
+    XformOps o;
+    o.gsz = 2;
+    o.rho_coef = ctx->cfg.density_prefactor / pow((double)ctx->n, (double)d);   // un-normalised inverse passes
+    std::vector<PassSpec> seq;
+    for (int a = d - 2; a >= 1; --a) seq.push_back(PassSpec{a, true, L_NONE, S_NONE});
+    seq.push_back(PassSpec{0, true, L_NONE, S_RHO_ONLY_FX});
+    int rc = run_passes(ctx, seq, ids, ns, ctx->Tscr, 0, ctx->Tscr, 0, o);
+    if (rc) return rc;
+    return poisson(ctx, (ns + 1) / 2, true, maxbits, /*x_fwd_done=*/true, false);
+}
+
+int fetch_pending_pmax(msm_ctx* ctx) {
+    if (ctx->pmax_pending.empty()) return MSM_OK;
+    const size_t n = ctx->pmax_pending.size();
+    if (cudaMemcpyAsync(ctx->h_scal + ctx->S + 2, ctx->maxbits, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->st) != cudaSuccess)
+        return fail(ctx, MSM_E_CUDA, "fetching max|phi| failed");
+    for (size_t i = 0; i < n; ++i) {
+        const int s = ctx->pmax_pending[i];
+        ctx->pmax_cache[s] = ctx->h_scal[ctx->S + 2 + i];
+        ctx->pmax_valid[s] = 1;
+    }
+    ctx->pmax_pending.clear();
+    return MSM_OK;
 }
 
 }  // namespace
@@ -678,6 +728,8 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     if (chunk > 1) chunk &= ~1;   // even, so that pairs never straddle chunks
     chunk = std::max(chunk, 1);
     ctx->chunk = chunk;
+    ctx->pmax_valid.assign(ctx->S, 0);
+    ctx->pmax_cache.assign(ctx->S, 0.0);
     ctx->in_k.assign(ctx->S, 0);
     ctx->has_psi.assign(ctx->S, 0);
     ctx->four_pi2 = (2.0 * M_PI) * (2.0 * M_PI);
@@ -728,7 +780,7 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     CUC(cudaMalloc(&ctx->maxbits, sizeof(unsigned long long) * (ctx->S + 2)));
     CUC(cudaMalloc(&ctx->scratch_small, sizeof(double) * 4096));
     CUC(cudaMallocHost(&ctx->h_dtab, sizeof(double2) * n * ctx->S));
-    CUC(cudaMallocHost(&ctx->h_scal, sizeof(double) * 2 * (ctx->S + 2)));
+    CUC(cudaMallocHost(&ctx->h_scal, sizeof(double) * 2 * (ctx->S + 2)));   // [0, S+2): alias / max ; [S+2, ..): eager max
     ctx->bytes = cb * (ctx->S + chunk + npair) + sizeof(double2) * n * (ctx->S + 1) + sizeof(double) * n +
                  sizeof(double) * (size_t)ctx->S * (glast.ntiles + 1) + 8 * (ctx->S + 2) + 8 * 4096;
     CUC(cudaMemsetAsync(ctx->alias_out, 0, sizeof(double) * ctx->S, ctx->st));
@@ -822,6 +874,7 @@ int msm_set_psi(msm_ctx* ctx, int32_t s, const double* psi) {
     CU(cudaStreamSynchronize(ctx->st));
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
+    ctx->pmax_valid[s] = 0;
     return MSM_OK;
 }
 
@@ -837,6 +890,7 @@ int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* 
     CU(cudaStreamSynchronize(ctx->st));
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
+    ctx->pmax_valid[s] = 0;
     return MSM_OK;
 }
 
@@ -928,11 +982,31 @@ int msm_potential_max(msm_ctx* ctx, const int32_t* active, double* out) {
     CU(cudaSetDevice(ctx->cfg.device));
     std::vector<int> ids = active_list(ctx, active);
     if (ids.empty()) return MSM_OK;
-    int rc = ensure_kspace(ctx, ids);
+    int rc = fetch_pending_pmax(ctx);
+    if (rc) return rc;
+    {
+        bool all = true;
+        for (int s : ids) all = all && ctx->pmax_valid[s];
+        if (all) {   // computed eagerly by the last msm_step
+            for (int s : ids) out[s] = ctx->pmax_cache[s];
+            return MSM_OK;
+        }
+    }
+    rc = ensure_kspace(ctx, ids);
     if (rc) return rc;
     const bool summed = ctx->cfg.coupling == MSM_COUPLING_SUMMED;
     CU(cudaMemsetAsync(ctx->maxbits, 0, sizeof(unsigned long long) * (ctx->S + 2), ctx->st));
-    if (!summed) {
+    if (full_fusion(ctx)) {
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            XformOps o;   // inverse pass of the last axis, out of place into the scratch slots
+            std::vector<PassSpec> first{PassSpec{ctx->dims - 1, true, L_NONE, S_NONE}};
+            rc = run_passes(ctx, first, &ids[i], ns, ctx->X, 1, ctx->Tscr, 0, o);
+            if (rc) return rc;
+            rc = dt_potential_tail(ctx, &ids[i], ns, ctx->maxbits + i);
+            if (rc) return rc;
+        }
+    } else if (!summed) {
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
             rc = density_from_psik(ctx, &ids[i], ns, false, false);
@@ -953,7 +1027,11 @@ int msm_potential_max(msm_ctx* ctx, const int32_t* active, double* out) {
     }
     CU(cudaMemcpyAsync(ctx->h_scal, ctx->maxbits, sizeof(double) * ids.size(), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
-    for (size_t i = 0; i < ids.size(); ++i) out[ids[i]] = summed ? ctx->h_scal[0] : ctx->h_scal[i];
+    for (size_t i = 0; i < ids.size(); ++i) {
+        out[ids[i]] = summed ? ctx->h_scal[0] : ctx->h_scal[i];
+        ctx->pmax_cache[ids[i]] = out[ids[i]];
+        ctx->pmax_valid[ids[i]] = 1;
+    }
     return MSM_OK;
 }
 
@@ -1046,7 +1124,46 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
         o.p_summed = summed ? 1 : 0;
         return run_transform(ctx, false, cid, ns, ctx->X, 1, ctx->X, 1, o);
     };
-    if (!summed) {
+    for (int s : ids) ctx->pmax_valid[s] = 0;
+    ctx->pmax_pending.clear();
+    if (full_fusion(ctx)) {
+        // 14 launches per chunk instead of 21, 384 instead of 480 algorithmic bytes per cell-update
+        const int d = ctx->dims;
+        CU(cudaMemsetAsync(ctx->maxbits, 0, sizeof(unsigned long long) * (ctx->S + 2), ctx->st));
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            const int* cid = &ids[i];
+            {   // drift + inverse (in place); the x pass also forward-transforms rho_a + i rho_b into the pair buffer
+                XformOps o;
+                o.gsz = 2;
+                o.rho_coef = ctx->cfg.density_prefactor;
+                std::vector<PassSpec> seq;
+                for (int a = d - 1; a >= 1; --a) seq.push_back(PassSpec{a, true, L_DRIFT, S_NONE});
+                seq.push_back(PassSpec{0, true, L_DRIFT, S_RHO_KEEP_FX});
+                if ((rc = run_passes(ctx, seq, cid, ns, ctx->X, 1, ctx->X, 1, o))) return rc;
+            }
+            if ((rc = poisson(ctx, (ns + 1) / 2, false, nullptr, /*x_fwd_done=*/true, /*x_inv_skip=*/true))) return rc;
+            {   // (inverse x of phi) + kick + forward + drift + alias; the last pass also starts the next dt-potential
+                XformOps o;
+                double kk[MAX_CHUNK];
+                for (int j = 0; j < ns; ++j) kk[j] = kick[cid[j]];
+                o.gsz = 2;
+                o.kick = kk;
+                o.dst2 = ctx->Tscr;
+                std::vector<PassSpec> seq;
+                if (d == 1) seq.push_back(PassSpec{0, false, L_KICK_IX, S_DRIFT_ALIAS_IZ});
+                else {
+                    seq.push_back(PassSpec{0, false, L_KICK_IX, S_DRIFT});
+                    for (int a = 1; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_DRIFT});
+                    seq.push_back(PassSpec{d - 1, false, L_NONE, S_DRIFT_ALIAS_IZ});
+                }
+                if ((rc = run_passes(ctx, seq, cid, ns, ctx->X, 1, ctx->X, 1, o))) return rc;
+            }
+            // potential of the NEW psi_k (the reference computes it at the start of the next update(), :497)
+            if ((rc = dt_potential_tail(ctx, cid, ns, ctx->maxbits + i))) return rc;
+        }
+        ctx->pmax_pending = ids;
+    } else if (!summed) {
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
             if ((rc = drift_inverse(&ids[i], ns, false))) return rc;
@@ -1073,6 +1190,7 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
     CU(cudaGetLastError());
     if (alias_mass) {
         CU(cudaMemcpyAsync(ctx->h_scal, ctx->alias_out, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->st));
+        if ((rc = fetch_pending_pmax(ctx))) return rc;   // same sync
         CU(cudaStreamSynchronize(ctx->st));
         for (int s : ids) alias_mass[s] = ctx->h_scal[s];
     }
@@ -1198,6 +1316,7 @@ int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double*
     if (rc) return rc;
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
+    ctx->pmax_valid[s] = 0;
     return MSM_OK;
 }
 
@@ -1213,6 +1332,7 @@ int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t s, double axis_length, double 
     if (rc) return rc;
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
+    ctx->pmax_valid[s] = 0;
     return MSM_OK;
 }
 
@@ -1225,6 +1345,7 @@ int msm_ic_copy(msm_ctx* ctx, int32_t dst, int32_t src) {
                            cudaMemcpyDeviceToDevice, ctx->st));
     ctx->in_k[dst] = ctx->in_k[src];
     ctx->has_psi[dst] = 1;
+    ctx->pmax_valid[dst] = 0;
     return MSM_OK;
 }
 
@@ -1238,6 +1359,7 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     CU(cudaSetDevice(ctx->cfg.device));
     const double sqrt_dv = sqrt(pow(ctx->cfg.dx, (double)ctx->dims));
     const double div = sqrt(n_tot) * (scheme == MSM_SCHEME_WIGNER ? 2.0 : sqrt(2.0));   // ics.rs:581 / :625
+    ctx->pmax_valid[s] = 0;
     k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div, ctx->n, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());

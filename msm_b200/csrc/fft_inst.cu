@@ -68,6 +68,8 @@ int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, bool p
     CASE(true, L_NONE, S_MAX)
     CASE(true, L_DRIFT, S_NONE)
     CASE(true, L_DRIFT, S_RHO_KEEP)
+    CASE(true, L_NONE, S_RHO_ONLY_FX)
+    CASE(true, L_DRIFT, S_RHO_KEEP_FX)
     // forward transforms
     CASE(false, L_NONE, S_NONE)
     CASE(false, L_NONE, S_SCALE)
@@ -77,6 +79,9 @@ int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, bool p
     CASE(false, L_NONE, S_POISSON_INV)
     CASE(false, L_KICK, S_DRIFT)
     CASE(false, L_KICK, S_DRIFT_ALIAS)
+    CASE(false, L_KICK_IX, S_DRIFT)
+    CASE(false, L_KICK_IX, S_DRIFT_ALIAS_IZ)
+    CASE(false, L_NONE, S_DRIFT_ALIAS_IZ)
 #undef CASE
     return -1;
 }

@@ -26,7 +26,13 @@ namespace msm {
 
 constexpr int MAX_CHUNK = 16;   // streams per launch group
 
-enum LoadOp { L_NONE = 0, L_DRIFT = 1, L_KICK = 2 };
+enum LoadOp {
+    L_NONE = 0,
+    L_DRIFT = 1,
+    L_KICK = 2,
+    L_KICK_IX = 3   // L_KICK, but the pair buffer holds phi BEFORE its last inverse pass: that pass runs here, on the
+                    // same lines, so phi never travels to HBM in real space
+};
 enum StoreOp {
     S_NONE = 0,         // plain store
     S_SCALE = 1,        // * scale
@@ -36,6 +42,10 @@ enum StoreOp {
     S_RHO_ONLY = 5,     // rho only, psi is not written            (potential at time t: only max|phi| is needed)
     S_POISSON = 6,      // * poisson_coef / k^2, DC -> 0           (last forward pass of the Poisson solve)
     S_MAX = 7,          // no store, max|re| and max|im|           (last inverse pass of the dt Poisson solve)
+    S_RHO_KEEP_FX = 9,  // S_RHO_KEEP / S_RHO_ONLY, then the FORWARD transform of the pair rho_a + i rho_b on the same
+    S_RHO_ONLY_FX = 10, // lines: the pair buffer receives rho after the first pass of the Poisson solve
+    S_DRIFT_ALIAS_IZ = 11,  // S_DRIFT_ALIAS, then the INVERSE transform of the stored psi_k into dst2 (first pass of the
+                            // next dt-potential)
     S_POISSON_INV = 8   // S_POISSON, then the INVERSE transform of the same lines, then store: the last forward
                         // and first inverse pass of the Poisson solve share their tile, so the k-space potential
                         // never travels to HBM
@@ -44,6 +54,7 @@ enum StoreOp {
 struct PassParams {
     const double2* src;
     double2* dst;
+    double2* dst2;                        // S_DRIFT_ALIAS_IZ: scratch slot per local index
     long long src_sstride, dst_sstride;   // elements between stream slots
     int src_by_sid, dst_by_sid;           // slot = stream id (resident array) or local index (scratch)
     int ns, gsz;                          // streams in this launch, streams per CTA group
@@ -311,10 +322,41 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
 }
 
 template <int LOP, int SOP> constexpr bool uses_stash() {
-    return LOP == L_KICK || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY || SOP == S_POISSON_INV;
+    return LOP == L_KICK || LOP == L_KICK_IX || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY || SOP == S_POISSON_INV ||
+           SOP == S_RHO_KEEP_FX || SOP == S_RHO_ONLY_FX;
+}
+constexpr bool sop_is_rho(int sop) {
+    return sop == S_RHO_KEEP || sop == S_RHO_ONLY || sop == S_RHO_KEEP_FX || sop == S_RHO_ONLY_FX;
+}
+constexpr bool sop_is_alias(int sop) { return sop == S_DRIFT_ALIAS || sop == S_DRIFT_ALIAS_IZ; }
+constexpr bool sop_needs_k2(int sop) { return sop_is_alias(sop) || sop == S_POISSON || sop == S_POISSON_INV; }
+
+// Each thread holds the elements e = t + NT * m (m = 0..E-1) of its line both as inputs of the first stage
+// (slot c * R0 + n  <->  m = n * (E / R0) + c) and as outputs of the last stage (slot c * RL + k  <->
+// m = c + (E / RL) * k).  Chaining a second transform on the same lines is therefore a compile-time register
+// permutation, no data exchange.
+template <int N> struct Slots {
+    using PL = Plan<N>;
+    static constexpr int E = PL::E, R0 = PL::R[0], RL = PL::R[PL::NS - 1];
+    static constexpr int in_slot_m(int slot) { return (slot % R0) * (E / R0) + slot / R0; }
+    static constexpr int out_slot_of_m(int m) { return (m % (E / RL)) * RL + m / (E / RL); }
+    static constexpr bool identity = (R0 == E && RL == E);
+};
+template <int N> __device__ __forceinline__ void outputs_to_inputs(double2 (&v)[Plan<N>::E]) {
+    if constexpr (!Slots<N>::identity) {
+        double2 w[Plan<N>::E];
+#pragma unroll
+        for (int i = 0; i < Plan<N>::E; ++i) w[i] = v[Slots<N>::out_slot_of_m(Slots<N>::in_slot_m(i))];
+#pragma unroll
+        for (int i = 0; i < Plan<N>::E; ++i) v[i] = w[i];
+    }
+}
+// exchange region in double2 units; single-stage plans (N <= 8) have no exchange, but L_KICK_IX parks phi_a there
+template <int N, int LOP> constexpr int exchange_elems() {
+    return Plan<N>::NS > 1 ? N * Plan<N>::T : (LOP == L_KICK_IX ? (Plan<N>::E * Plan<N>::THREADS + 1) / 2 : 0);
 }
 template <int N, int LOP, int SOP> constexpr size_t pass_smem_bytes() {
-    return (Plan<N>::NS > 1 ? sizeof(double2) * N * Plan<N>::T : 0) +
+    return sizeof(double2) * exchange_elems<N, LOP>() +
            (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * Plan<N>::THREADS : 0);
 }
 
@@ -332,7 +374,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     extern __shared__ double2 sm[];
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
-    double* stash = reinterpret_cast<double*>(sm + (PL::NS > 1 ? N * T : 0));
+    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP>());
     __shared__ double red[2][32], red2[32];
     double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
     int item_parity = 0;
@@ -372,7 +414,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
     double kline = 0.0;
     int c0 = 0, c1 = 0, c2 = 0;
-    if constexpr (SOP == S_DRIFT_ALIAS || SOP == S_POISSON || SOP == S_POISSON_INV) {
+    if constexpr (sop_needs_k2(SOP)) {
         const int n = p.n;
         if (p.axis == 0) {
             const int line = tile * T + l;   // row index in the (blocked) device layout, see core.cu blk_index
@@ -428,11 +470,33 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
             if (ntile < p.ntiles && (same_tile || ti + 1 < p.tiles_per_cta)) {
                 const int ns_ = p.sid[nli];
                 prefetch_tile(p.src + (long long)(p.src_by_sid ? ns_ : nli) * p.src_sstride, ntile);
-                if (LOP == L_KICK && !same_tile) prefetch_tile(pb, ntile);
+                if ((LOP == L_KICK || LOP == L_KICK_IX) && !same_tile) prefetch_tile(pb, ntile);
             }
         }
 
         double2 v[E];
+        if constexpr (LOP == L_KICK_IX) {
+            // last inverse pass of the Poisson solve on this tile of the pair buffer, once per unit; phi_a is parked in
+            // the (still idle) exchange buffer, phi_b in the stash, each thread in its own slots
+            if (q == 0) {
+#pragma unroll
+                for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                    for (int n = 0; n < R0; ++n) {
+                        const int e = n * M0 + t + NT * c;
+                        v[c * R0 + n] = lv ? pb[base + along(e)] : make_double2(0.0, 0.0);
+                    }
+                }
+                run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+                outputs_to_inputs<N>(v);
+                double* phia = reinterpret_cast<double*>(sm);
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    phia[i * THREADS + tid] = v[i].x;
+                    stash[i * THREADS + tid] = p.p_summed ? v[i].x : v[i].y;
+                }
+            }
+        }
         // ---- load (stage-0 input order): all global loads first, operators afterwards ----
 #pragma unroll
         for (int c = 0; c < NB0; ++c) {
@@ -455,6 +519,17 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                     v[c * R0 + n] = cmul(v[c * R0 + n], w);
                 }
             }
+        }
+        if constexpr (LOP == L_KICK_IX) {
+            const double* phia = reinterpret_cast<const double*>(sm);
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const double ph = (q == 0) ? phia[i * THREADS + tid] : stash[i * THREADS + tid];
+                double sn, cs;
+                kick_sincos(-p.kick[li] * ph, &sn, &cs);
+                v[i] = cmul(v[i], make_double2(cs, sn));
+            }
+            if (q == 0) __syncthreads();   // phi_a lives in the exchange buffer: everyone reads before anyone scatters
         }
         if constexpr (LOP == L_KICK) {
             // psi *= exp(-i kappa phi)    (simulation_object.rs:535-545); phi_a + i phi_b is read once per pair
@@ -496,24 +571,8 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                     v[c * RL + k].y *= m;
                 }
             }
-            const double2* tw2 = data_dependent(p.twiddle, v[0].x, p.zero);   // v[0] is the multiplied value here
-            if constexpr (R0 == E && RL == E) {
-                run_stages<N, !INV, XL, 0>(v, sm, t, l, tw2);   // register orders coincide (e.g. 512 = 8*8*8)
-            } else {
-                double2 w[E];
-#pragma unroll
-                for (int c = 0; c < NB0; ++c) {
-#pragma unroll
-                    for (int n = 0; n < R0; ++n) {
-                        constexpr int PER = E / RL;           // output slot of element index m: (m % PER) * RL + m / PER
-                        const int m = n * (E / R0) + c;
-                        w[c * R0 + n] = v[(m % PER) * RL + m / PER];
-                    }
-                }
-                run_stages<N, !INV, XL, 0>(w, sm, t, l, tw2);
-#pragma unroll
-                for (int j = 0; j < E; ++j) v[j] = w[j];
-            }
+            outputs_to_inputs<N>(v);
+            run_stages<N, !INV, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
         }
 
         // ---- store (last-stage output order) ----
@@ -529,11 +588,11 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                     x.x *= p.scale;
                     x.y *= p.scale;
                 }
-                if constexpr (SOP == S_DRIFT || SOP == S_DRIFT_ALIAS) {
+                if constexpr (SOP == S_DRIFT || sop_is_alias(SOP)) {
                     const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
                     x = cmul(x, w);
                 }
-                if constexpr (SOP == S_DRIFT_ALIAS) {
+                if constexpr (sop_is_alias(SOP)) {
                     // check_alias: sum |psi_k|^2 where k^2 > k2_cutoff * k2_max  (simulation_object.rs:1259-1280)
                     if (lv && k2_of(e) > p.alias_k2_thresh) acc += x.x * x.x + x.y * x.y;
                 }
@@ -548,27 +607,62 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
                     acc = fmax(acc, fabs(x.x));
                     acc2 = fmax(acc2, fabs(x.y));
                 }
-                if constexpr (SOP == S_RHO_KEEP || SOP == S_RHO_ONLY) {
+                if constexpr (sop_is_rho(SOP)) {
                     // rho = A real(psi conj(psi))   (simulation_object.rs:1051-1062)
+                    constexpr bool FX = (SOP == S_RHO_KEEP_FX || SOP == S_RHO_ONLY_FX);
                     const double rho = p.rho_coef * (x.x * x.x + x.y * x.y);
                     double* slot = &stash[(c * RL + k) * THREADS + tid];
+                    double2 pair = make_double2(0.0, 0.0);
                     if (!p.p_summed) {
-                        // pair buffer rho_a + i rho_b: the first stream parks its value, the second writes both
+                        // pair buffer rho_a + i rho_b: the first stream parks its value, the second completes the pair
                         if (!last_of_group) *slot = rho;
-                        else if (lv) pb[off] = (q == 0) ? make_double2(rho, 0.0) : make_double2(*slot, rho);
+                        else pair = (q == 0) ? make_double2(rho, 0.0) : make_double2(*slot, rho);
                     } else {
                         const double sum = (q == 0) ? rho : *slot + rho;
                         if (!last_of_group) *slot = sum;
-                        else if (lv) pb[off] = make_double2(p.rho_accumulate ? pb[off].x + sum : sum, 0.0);
+                        else pair = make_double2((p.rho_accumulate && lv) ? pb[off].x + sum : sum, 0.0);
                     }
+                    if (SOP != S_RHO_ONLY && SOP != S_RHO_ONLY_FX) {
+                        if (lv) dst[off] = x;
+                    }
+                    if (FX) v[c * RL + k] = pair;               // transformed below, after psi has been stored
+                    else if (last_of_group && lv) pb[off] = pair;
                 }
-                if constexpr (SOP != S_RHO_ONLY && SOP != S_MAX) {
+                if constexpr (!sop_is_rho(SOP) && SOP != S_MAX) {
                     if (lv) dst[off] = x;
                 }
+                if constexpr (SOP == S_DRIFT_ALIAS_IZ) v[c * RL + k] = x;   // psi_k as stored; transformed back below
             }
         }
 
-        if constexpr (SOP == S_DRIFT_ALIAS) {
+        if constexpr (SOP == S_RHO_KEEP_FX || SOP == S_RHO_ONLY_FX) {
+            // first (x) pass of the Poisson solve on the finished pair rho_a + i rho_b, same lines: forward transform
+            if (last_of_group) {
+                outputs_to_inputs<N>(v);
+                run_stages<N, false, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+#pragma unroll
+                for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+                    for (int k = 0; k < RL; ++k) {
+                        if (lv) pb[base + along(t + NT * c + LL * k)] = v[c * RL + k];
+                    }
+                }
+            }
+        }
+        if constexpr (SOP == S_DRIFT_ALIAS_IZ) {
+            // first pass of the next dt-potential: inverse transform of the psi_k just stored, into the scratch slot
+            double2* __restrict__ d2 = p.dst2 + (long long)li * p.dst_sstride;
+            outputs_to_inputs<N>(v);
+            run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+#pragma unroll
+            for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+                for (int k = 0; k < RL; ++k) {
+                    if (lv) d2[base + along(t + NT * c + LL * k)] = v[c * RL + k];
+                }
+            }
+        }
+        if constexpr (sop_is_alias(SOP)) {
             // one partial per (stream, tile), summed in a fixed order -> deterministic.  `red` is double buffered by
             // item parity: by the time a parity is reused the stage barriers of the item in between have passed.
             acc = warp_sum(acc);
