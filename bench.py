@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-ALG_BYTES_PER_CELL_UPDATE = 480.0       # DESIGN.md section 3 (independent streams, 3-pass transforms)
+ALG_BYTES_PER_CELL_UPDATE = 480.0       # SURVEY 8d / DESIGN.md section 3: 3-pass transforms, un-fused pass boundaries
 
 
 def alg_bytes(coupling, s_local):
@@ -144,7 +144,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "cell-updates/s", "value": rate, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.size}^3 x {args.streams} streams fp64 static box"},
+            "config": {"workload": f"synthetic {args.size}^3 x {args.streams} streams fp64 static box (BASELINE configs[4])",
+                       "coupling": args.coupling},
             "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                              "sample": f"1 stream x {size}^3 per step, NumPy/pocketfft restatement of update()"},
             "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

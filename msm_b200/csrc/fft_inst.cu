@@ -17,7 +17,7 @@ template <bool INV, int LOP, int SOP, bool XL>
 int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
     using PL = Plan<N>;
     static bool configured = false;
-    const size_t smem = pass_smem_bytes<N, LOP, SOP>();
+    const size_t smem = pass_smem_bytes<N, LOP, SOP, XL>();
     auto kern = fft_pass_kernel<N, INV, LOP, SOP, XL>;
     if (!configured) {
         if (smem > 32 * 1024) {   // static __shared__ (reduction scratch) counts towards the 48 KiB default

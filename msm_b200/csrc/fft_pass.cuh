@@ -268,11 +268,14 @@ __device__ __forceinline__ double warp_max(double x) {
 //
 // Two thread <-> data mappings (template flag XL):
 //   XL = false (strided axes)   tid = t * T + l, exchange buffer [position][line]
-//   XL = true  (contiguous axis) tid = l * NT + t, exchange buffer [line][position ^ swizzle]: a warp then reads 32
-//              consecutive elements of ONE line (512 contiguous bytes); the XOR of the low 3 position bits with bits
-//              3..5 keeps the stride-8 gather of the last stage conflict free.
+//   XL = true  (contiguous axis) tid = l * NT + t, exchange buffer [line][position + position / 8]: a warp then reads
+//              32 consecutive elements of ONE line (512 contiguous bytes); the padding keeps the stride-8 gather of
+//              the last stage conflict free.
 template <int N, bool XL> __device__ __forceinline__ int sm_index(int pos, int l) {
-    if (XL) return l * N + (pos ^ ((pos >> 3) & 7));
+    // contiguous axis: one 16-byte pad after every 8 positions.  The stride-8 gather of the last stage becomes
+    // stride 9 (conflict free) and -- unlike an XOR swizzle -- every compile-time part of `pos` stays an additive
+    // immediate, so a thread needs one base register per stage instead of one per access.
+    if (XL) return l * (N + N / 8) + pos + (pos >> 3);
     return pos * Plan<N>::T + l;
 }
 
@@ -352,11 +355,12 @@ template <int N> __device__ __forceinline__ void outputs_to_inputs(double2 (&v)[
     }
 }
 // exchange region in double2 units; single-stage plans (N <= 8) have no exchange, but L_KICK_IX parks phi_a there
-template <int N, int LOP> constexpr int exchange_elems() {
-    return Plan<N>::NS > 1 ? N * Plan<N>::T : (LOP == L_KICK_IX ? (Plan<N>::E * Plan<N>::THREADS + 1) / 2 : 0);
+template <int N, int LOP, bool XL> constexpr int exchange_elems() {
+    return Plan<N>::NS > 1 ? (XL ? (N + N / 8) : N) * Plan<N>::T
+                           : (LOP == L_KICK_IX ? (Plan<N>::E * Plan<N>::THREADS + 1) / 2 : 0);
 }
-template <int N, int LOP, int SOP> constexpr size_t pass_smem_bytes() {
-    return sizeof(double2) * exchange_elems<N, LOP>() +
+template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {
+    return sizeof(double2) * exchange_elems<N, LOP, XL>() +
            (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * Plan<N>::THREADS : 0);
 }
 
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kern
     extern __shared__ double2 sm[];
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
-    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP>());
+    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>());
     __shared__ double red[2][32], red2[32];
     double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
     int item_parity = 0;
