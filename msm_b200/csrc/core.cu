@@ -52,6 +52,16 @@ int plan_radices(int n, int r[4]) {
     return 0;
 }
 
+template <int N> static int tx_of() { return tile_T<N, true>(); }
+int plan_tx(int n) {
+    switch (n) {
+#define C(N) case N: return tx_of<N>();
+        C(2) C(4) C(8) C(16) C(32) C(64) C(128) C(256) C(512) C(1024)
+#undef C
+    }
+    return 0;
+}
+
 static int plan_T(int n) { return n >= 8 ? 8 : n; }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -278,7 +288,7 @@ struct ProfEvent {
 
 struct msm_ctx {
     msm_config cfg;
-    int n = 0, dims = 0, S = 0, chunk = 0, T = 0;
+    int n = 0, dims = 0, S = 0, chunk = 0, T = 0, TX = 0;   // tile heights: strided axes / contiguous axis
     int lb = 0;   // log2 of the slow-axis block (device layout, see blk_index)
     long long C = 0;
     cudaStream_t st = nullptr;
@@ -495,7 +505,7 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop;
         const bool inv = seq[k].inv;
         const bool pipe = ctx->pipe && ctx->n >= PIPE_MIN_N;
-        const Geom g = make_geom(ctx, axis, pipe ? PIPE_T : ctx->T);
+        const Geom g = make_geom(ctx, axis, pipe ? PIPE_T : (axis == 0 && ctx->xl) ? ctx->TX : ctx->T);
         const bool first = (k == 0);
         p.src = first ? src : work;
         p.src_by_sid = first ? src_by_sid : work_by_sid;
@@ -712,6 +722,7 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     ctx->dims = cfg->dims;
     ctx->S = cfg->n_streams;
     ctx->T = plan_T(n);
+    ctx->TX = plan_tx(n);
     ctx->C = 1;
     for (int d = 0; d < cfg->dims; ++d) ctx->C *= n;
     ctx->launcher = get_pass_launcher(n);
@@ -774,7 +785,8 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     CUC(cudaMalloc(&ctx->ksq, sizeof(double) * n));
     const Geom glast = make_geom(ctx, ctx->dims - 1, std::min(ctx->T, PIPE_T));   // finest tiling any kernel uses
     ctx->ntiles_last = glast.ntiles;
-    ctx->ntiles_used = make_geom(ctx, ctx->dims - 1, (ctx->pipe && n >= PIPE_MIN_N) ? PIPE_T : ctx->T).ntiles;
+    ctx->ntiles_used = make_geom(ctx, ctx->dims - 1, (ctx->pipe && n >= PIPE_MIN_N) ? PIPE_T
+                                                     : (ctx->dims == 1 && ctx->xl) ? ctx->TX : ctx->T).ntiles;
     CUC(cudaMalloc(&ctx->alias_partial, sizeof(double) * (size_t)ctx->S * glast.ntiles));
     CUC(cudaMalloc(&ctx->alias_out, sizeof(double) * ctx->S));
     CUC(cudaMalloc(&ctx->maxbits, sizeof(unsigned long long) * (ctx->S + 2)));

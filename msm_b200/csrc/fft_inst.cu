@@ -27,7 +27,7 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta, groups, 1);
-    kern<<<grid, PL::THREADS, smem, st>>>(p);
+    kern<<<grid, tile_threads<N, XL>(), smem, st>>>(p);
     return (int)cudaPeekAtLastError();
 }
 

@@ -113,6 +113,17 @@ MSM_PLAN(512,  8, 8,  2, 3, 8, 8, 8, 1)
 MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #undef MSM_PLAN
 
+// Tile height.  Strided axes need T = 8 lines (full 128-byte rows); on the contiguous axis lines are 16*N contiguous
+// bytes anyway, so large transforms use T = 4: half the shared memory and threads per CTA, twice the CTAs per SM --
+// the load / compute / store phases of four CTAs interleave better than those of two (matters most for the fused
+// two-transform kernels, all of which run on the contiguous axis or tolerate it).
+#ifndef MSM_TX
+#define MSM_TX 4
+#endif
+template <int N, bool XL> constexpr int tile_T() { return (XL && N >= 256 && Plan<N>::T == 8) ? MSM_TX : Plan<N>::T; }
+template <int N, bool XL> constexpr int tile_threads() { return Plan<N>::NT * tile_T<N, XL>(); }
+template <int N, bool XL> constexpr int tile_minb() { return Plan<N>::MINB * (Plan<N>::T / tile_T<N, XL>()); }
+
 template <int N> constexpr int plan_L(int q) {   // product of radices of stages < q
     int l = 1;
     for (int i = 0; i < q; ++i) l *= Plan<N>::R[i];
@@ -276,7 +287,7 @@ template <int N, bool XL> __device__ __forceinline__ int sm_index(int pos, int l
     // stride 9 (conflict free) and -- unlike an XOR swizzle -- every compile-time part of `pos` stays an additive
     // immediate, so a thread needs one base register per stage instead of one per access.
     if (XL) return l * (N + N / 8) + pos + (pos >> 3);
-    return pos * Plan<N>::T + l;
+    return pos * tile_T<N, false>() + l;
 }
 
 template <int N, bool INV, bool XL, int Q>
@@ -356,18 +367,18 @@ template <int N> __device__ __forceinline__ void outputs_to_inputs(double2 (&v)[
 }
 // exchange region in double2 units; single-stage plans (N <= 8) have no exchange, but L_KICK_IX parks phi_a there
 template <int N, int LOP, bool XL> constexpr int exchange_elems() {
-    return Plan<N>::NS > 1 ? (XL ? (N + N / 8) : N) * Plan<N>::T
-                           : (LOP == L_KICK_IX ? (Plan<N>::E * Plan<N>::THREADS + 1) / 2 : 0);
+    return Plan<N>::NS > 1 ? (XL ? (N + N / 8) : N) * tile_T<N, XL>()
+                           : (LOP == L_KICK_IX ? (Plan<N>::E * tile_threads<N, XL>() + 1) / 2 : 0);
 }
 template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {
     return sizeof(double2) * exchange_elems<N, LOP, XL>() +
-           (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * Plan<N>::THREADS : 0);
+           (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * tile_threads<N, XL>() : 0);
 }
 
 template <int N, bool INV, int LOP, int SOP, bool XL>
-__global__ void __launch_bounds__(Plan<N>::THREADS, Plan<N>::MINB) fft_pass_kernel(const PassParams p) {
+__global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft_pass_kernel(const PassParams p) {
     using PL = Plan<N>;
-    constexpr int E = PL::E, T = PL::T, NT = PL::NT, THREADS = PL::THREADS;
+    constexpr int E = PL::E, T = tile_T<N, XL>(), NT = PL::NT, THREADS = tile_threads<N, XL>();
     constexpr int R0 = PL::R[0];
     constexpr int M0 = N / R0;
     constexpr int NB0 = E / R0;
@@ -724,6 +735,8 @@ constexpr int PIPE_T = 4;         // lines per tile of the pipelined kernel
 pass_launcher_t get_pass_launcher(int n);
 // radices of the plan for length n (host side, for building the twiddle tables); returns the number of stages
 int plan_radices(int n, int radices[4]);
+// tile height of the contiguous-axis kernels for length n (host side)
+int plan_tx(int n);
 const char* pass_kernel_name(int n, bool inv, int lop, int sop);
 
 }  // namespace msm
