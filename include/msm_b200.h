@@ -151,6 +151,17 @@ int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t stream, double axis_length, do
 int msm_ic_copy(msm_ctx* ctx, int32_t dst_stream, int32_t src_stream);
 int msm_sample_perturbation(msm_ctx* ctx, int32_t stream, int32_t scheme, uint64_t seed, double n_tot);
 
+/* Ensemble statistics over streams (restates the reductions of the `synthesizer` crate,
+ * synthesizer/src/lib.rs:106-342 `analyze_sims` with the field closures of synthesizer/src/main.rs:63-93):
+ * SUMS over the selected local streams of   psi, |psi|^2, psi_k, |psi_k|^2   where psi_k is the UN-normalised forward
+ * DFT of psi (ndrustfft `ndfft` per axis, lib.rs:206-213 -- unlike the simulator's unitary transform).  Done on the
+ * device from the resident arrays, so S x dumps x 2 GiB of disk traffic disappears.  The caller divides by the global
+ * stream count (after summing over ranks) and forms  Qx = sum_cells(<|psi|^2> - |<psi>|^2) * dx^dims  (main.rs:161-173).
+ * msm_ensemble_get downloads one field (0 psi, 1 psi2, 2 psik, 3 psik2) as re / im planes in the host's linear layout;
+ * psi2 and psik2 are real (the reference writes an all-zero imaginary file); either pointer may be NULL. */
+int msm_ensemble_accumulate(msm_ctx* ctx, const int32_t* active);
+int msm_ensemble_get(msm_ctx* ctx, int32_t field, double* re, double* im);
+
 /* Per-kernel timing (CUDA events around every launch on the context's stream).  msm_profile_read returns up to
  * `cap` records; names are static strings. */
 typedef struct msm_profile_record {

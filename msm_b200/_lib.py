@@ -93,6 +93,8 @@ PROTOTYPES = {
     "msm_ic_spherical_tophat": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "msm_ic_copy": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "msm_sample_perturbation": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_double]),
+    "msm_ensemble_accumulate": (C.c_int, [_vp, _ip]),
+    "msm_ensemble_get": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_profile_enable": (C.c_int, [_vp, C.c_int32]),
     "msm_profile_read": (C.c_int, [_vp, C.POINTER(MsmProfileRecord), C.c_int32, _ip]),
     "msm_timer_start": (C.c_int, [_vp]),

@@ -197,6 +197,20 @@ class Context:
     def sample_perturbation(self, stream: int, scheme: str, seed: int, n_tot: float) -> None:
         self._chk(lib.msm_sample_perturbation(self.handle, stream, _lib.SCHEMES[scheme], int(seed), float(n_tot)))
 
+    # ensemble statistics (the synthesizer's stream reductions, on the device)
+    def ensemble_sums(self, active=None) -> Dict[str, np.ndarray]:
+        """SUMS over the selected streams of psi, |psi|^2, psi_k (un-normalised DFT), |psi_k|^2
+        (synthesizer/src/main.rs:63-93); divide by the global stream count for the synthesizer's means."""
+        keep, ptr = self._active(active)
+        self._chk(lib.msm_ensemble_accumulate(self.handle, ptr))
+        out = {}
+        for field, name in enumerate(("psi", "psi2", "psik", "psik2")):
+            re = np.empty(self.shape, dtype=np.float64)
+            im = np.empty(self.shape, dtype=np.float64)
+            self._chk(lib.msm_ensemble_get(self.handle, field, _f64(re.reshape(-1)), _f64(im.reshape(-1))))
+            out[name] = re + 1j * im
+        return out
+
     # profiling
     def profile_enable(self, on: bool = True) -> None:
         self._chk(lib.msm_profile_enable(self.handle, 1 if on else 0))

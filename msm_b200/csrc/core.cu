@@ -112,6 +112,32 @@ __global__ void k_extract(const double2* __restrict__ in, double* __restrict__ o
         out[i] = comp ? v.y : v.x;
     }
 }
+// sums over streams of v and |v|^2 (synthesizer/src/main.rs:63-93), streams added in list order -> deterministic.
+// All grids share the device layout, so the cell index needs no mapping.
+struct StreamList {
+    int n;
+    int id[msm::MAX_CHUNK];
+};
+__global__ void k_stream_sums(const double2* __restrict__ base, long long stride, StreamList sl, double2* __restrict__ sum,
+                              double* __restrict__ sum2, long long cells, double f1, double f2, int accumulate) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x) {
+        double2 a = accumulate ? sum[q] : make_double2(0.0, 0.0);
+        double b = accumulate ? sum2[q] : 0.0;
+        for (int i = 0; i < sl.n; ++i) {
+            const double2 v = base[(long long)sl.id[i] * stride + q];
+            a.x += f1 * v.x;
+            a.y += f1 * v.y;
+            b += f2 * (v.x * v.x + v.y * v.y);
+        }
+        sum[q] = a;
+        sum2[q] = b;
+    }
+}
+__global__ void k_real_to_planes(const double* __restrict__ in, double* __restrict__ re, long long cells, int n, int lb) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x)
+        re[q] = in[blk_index(q, n, lb)];
+}
+
 // alias_out[s] = dv * sum_tiles partial[s][tile]    (fixed summation order: deterministic)
 __global__ void k_alias_reduce(const double* __restrict__ partial, double* __restrict__ out, int ntiles, int pitch,
                                double dv) {
@@ -301,6 +327,8 @@ struct msm_ctx {
     double* h_scal = nullptr;    // pinned, 2*S doubles
     unsigned long long* maxbits = nullptr;
     double* scratch_small = nullptr;  // 4096 doubles
+    double2 *ens_psi = nullptr, *ens_psik = nullptr;   // ensemble sums (row f-3), allocated on first use
+    double *ens_psi2 = nullptr, *ens_psik2 = nullptr;
     std::vector<char> in_k, has_psi;
     // max|phi| of the CURRENT psi_k, computed eagerly at the end of msm_step (its first pass is fused into the step's
     // last pass); msm_potential_max returns it without touching the GPU while it is valid
@@ -850,6 +878,10 @@ void msm_destroy(msm_ctx* ctx) {
     cudaFree(ctx->alias_out);
     cudaFree(ctx->maxbits);
     cudaFree(ctx->scratch_small);
+    cudaFree(ctx->ens_psi);
+    cudaFree(ctx->ens_psik);
+    cudaFree(ctx->ens_psi2);
+    cudaFree(ctx->ens_psik2);
     if (ctx->h_dtab) cudaFreeHost(ctx->h_dtab);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->dtab_done) cudaEventDestroy(ctx->dtab_done);
@@ -1375,6 +1407,77 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div, ctx->n, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());
+    return MSM_OK;
+}
+
+// ---- ensemble statistics (row f-3) ---------------------------------------------------------------------------
+int msm_ensemble_accumulate(msm_ctx* ctx, const int32_t* active) {
+    if (!ctx) return MSM_E_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    std::vector<int> ids = active_list(ctx, active);
+    if (ids.empty()) return fail(ctx, MSM_E_ARG, "msm_ensemble_accumulate: no stream selected");
+    int rc = ensure_kspace(ctx, ids);
+    if (rc) return rc;
+    if (!ctx->ens_psi) {
+        const size_t cb = sizeof(double2) * (size_t)ctx->C;
+        cudaError_t e = cudaMalloc(&ctx->ens_psi, cb);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->ens_psik, cb);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->ens_psi2, cb / 2);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->ens_psik2, cb / 2);
+        if (e != cudaSuccess) return fail(ctx, MSM_E_NOMEM, std::string("ensemble grids: ") + cudaGetErrorString(e));
+        ctx->bytes += 3 * cb;
+    }
+    const double nd = pow((double)ctx->n, (double)ctx->dims);
+    for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+        const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+        StreamList byid{ns, {0}}, local{ns, {0}};
+        for (int j = 0; j < ns; ++j) {
+            byid.id[j] = ids[i + j];
+            local.id[j] = j;
+        }
+        // psi_k as the synthesizer defines it: un-normalised DFT of psi = n^(d/2) * (resident unitary psi_k)
+        {
+            ProfScope ps(ctx, "ensemble_sums", 16.0 * ctx->C * ns);
+            k_stream_sums<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X, ctx->C, byid, ctx->ens_psik, ctx->ens_psik2, ctx->C,
+                                                                   sqrt(nd), nd, i > 0);
+        }
+        ctx->launches++;
+        CU(cudaGetLastError());
+        // psi = unitary inverse transform of the resident psi_k, into the scratch slots
+        XformOps o;
+        o.sop_each = o.sop_last = S_SCALE;
+        o.scale = 1.0 / sqrt((double)ctx->n);
+        rc = run_transform(ctx, true, &ids[i], ns, ctx->X, 1, ctx->Tscr, 0, o);
+        if (rc) return rc;
+        {
+            ProfScope ps(ctx, "ensemble_sums", 16.0 * ctx->C * ns);
+            k_stream_sums<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->Tscr, ctx->C, local, ctx->ens_psi, ctx->ens_psi2, ctx->C, 1.0,
+                                                                   1.0, i > 0);
+        }
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return MSM_OK;
+}
+
+int msm_ensemble_get(msm_ctx* ctx, int32_t field, double* re, double* im) {
+    if (!ctx || field < 0 || field > 3) return fail(ctx, MSM_E_ARG, "msm_ensemble_get: bad argument");
+    if (!ctx->ens_psi) return fail(ctx, MSM_E_STATE, "msm_ensemble_get: call msm_ensemble_accumulate first");
+    CU(cudaSetDevice(ctx->cfg.device));
+    double* planes = reinterpret_cast<double*>(ctx->P);   // 2*C doubles of staging
+    if (field == 0 || field == 2) {
+        k_deinterleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(field == 0 ? ctx->ens_psi : ctx->ens_psik, planes, planes + ctx->C,
+                                                              ctx->C, ctx->n, ctx->lb);
+    } else {
+        k_real_to_planes<<<grid_for(ctx->C), 256, 0, ctx->st>>>(field == 1 ? ctx->ens_psi2 : ctx->ens_psik2, planes, ctx->C,
+                                                                ctx->n, ctx->lb);
+        CU(cudaMemsetAsync(planes + ctx->C, 0, sizeof(double) * (size_t)ctx->C, ctx->st));
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (re) CU(cudaMemcpyAsync(re, planes, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    if (im) CU(cudaMemcpyAsync(im, planes + ctx->C, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
     return MSM_OK;
 }
 

@@ -97,3 +97,28 @@ def main(argv=None) -> int:
     if args.verbose or len(cfg.streams) > 1:
         print(f"Finished all streams in {res['seconds']:.0f} seconds")
     return 0
+
+
+def combine_streams(sim: SimulationObject, n_streams_global: int, dx: float, active=None) -> dict:
+    """The synthesizer's per-dump products from the resident wavefunctions (synthesizer/src/lib.rs:106-342,
+    main.rs:63-93,161-173): means over streams of psi, |psi|^2, psi_k, |psi_k|^2 and Qx = sum(<|psi|^2> - |<psi>|^2) dV.
+    With several ranks, sum the four arrays over ranks before dividing (they are plain sums)."""
+    sums = sim.grid.ensemble_sums(active)
+    means = {k: v / float(n_streams_global) for k, v in sums.items()}
+    dv = dx ** sim.parameters.dims
+    means["Qx"] = complex(np.sum(means["psi2"] - means["psi"] * np.conj(means["psi"])) * dv)
+    return means
+
+
+def write_combined(root: str, sim_name: str, dump_index: int, means: dict, dims: int, size: int) -> None:
+    """`<root>/<sim>-combined/{psi,psi2,psik,psik2,Qx}_%05d_real|_imag`, NPY, the layout of `dump_complex`
+    (synthesizer/src/lib.rs:70-102,282-330)."""
+    d = os.path.join(root, f"{sim_name}-combined")
+    os.makedirs(d, exist_ok=True)
+    shape = (size, size if dims >= 2 else 1, size if dims == 3 else 1, 1)
+    for name, arr in means.items():
+        a = np.asarray(arr, dtype=np.complex128)
+        a = a.reshape(shape) if a.size > 1 else a.reshape(1, 1, 1, 1)
+        for part, data in (("real", a.real), ("imag", a.imag)):
+            with open(os.path.join(d, f"{name}_{dump_index:05d}_{part}"), "wb") as f:
+                np.lib.format.write_array(f, np.ascontiguousarray(data, dtype=np.float64), version=(1, 0))

@@ -739,6 +739,22 @@ def write_dump(root: str, sim_name: str, dump_index: int, psi: np.ndarray, dims:
 
 
 # --------------------------------------------------------------------------------------
+# synthesizer reductions  (synthesizer/src/lib.rs:106-342, synthesizer/src/main.rs:63-93,161-173)
+# --------------------------------------------------------------------------------------
+def synthesizer_combine(psis: Sequence[np.ndarray], dv: float) -> dict:
+    """`analyze_sims`: means over the `-stream*` runs of psi, |psi|^2, psi_k, |psi_k|^2 with psi_k the UN-normalised
+    forward DFT (ndrustfft `ndfft` per axis, lib.rs:206-213), and `post_combine`'s Qx = sum(psi2 - |psi|^2) * dv."""
+    n = float(len(psis))
+    psi = sum(psis) / n                                                         # main.rs:74-77
+    psi2 = sum(p * np.conj(p) for p in psis) / n                                # main.rs:78-81
+    pk = [_fft.fftn(p, workers=_WORKERS) for p in psis]                         # lib.rs:206-213 (no normalisation)
+    psik = sum(pk) / n                                                          # main.rs:82-85
+    psik2 = sum(k * np.conj(k) for k in pk) / n                                 # main.rs:86-92
+    qx = complex(np.sum(psi2 - psi * np.conj(psi)) * dv)                        # main.rs:161-173
+    return {"psi": psi, "psi2": psi2, "psik": psik, "psik2": psik2, "Qx": qx}
+
+
+# --------------------------------------------------------------------------------------
 # the north_star's second coupling mode (NOT in the reference, SURVEY.md section 0 D1)
 # --------------------------------------------------------------------------------------
 class SummedEnsemble:

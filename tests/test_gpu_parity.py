@@ -451,3 +451,32 @@ def _oracle_potential(p, psi):
     s = o.SimulationObject(p, psi)
     s.calculate_potential()
     return s.phi.real
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# row f-3: the synthesizer's stream reductions on the device
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lb", [0, 2])
+def test_ensemble_statistics_match_synthesizer_restatement(monkeypatch, tmp_path, lb):
+    from msm_b200 import driver
+    monkeypatch.setenv("MSM_B200_LB", str(lb))
+    ps = oracle_streams("spherical-tophat", limit=5)
+    sim, refs, worst = run_both(ps, 3, chunk=2)
+    want = o.synthesizer_combine([r.psi for r in refs], ps[0].dx ** 3)
+    got = driver.combine_streams(sim, 5, ps[0].dx)
+    for k in ("psi", "psi2", "psik", "psik2"):
+        assert rel_l2(got[k], want[k]) < 1e-12, k
+        if k in ("psi2", "psik2"):
+            assert np.max(np.abs(got[k].imag)) == 0.0
+    # Qx is a difference of O(1) terms (it is ~0 for these nearly identical streams): compare on that scale
+    assert abs(got["Qx"] - want["Qx"]) <= 1e-12 * abs(np.sum(want["psi2"]) * ps[0].dx ** 3)
+    # a subset of streams, and the on-disk layout of dump_complex
+    sub = driver.combine_streams(sim, 2, ps[0].dx, active=[1, 0, 0, 1, 0])
+    want2 = o.synthesizer_combine([refs[0].psi, refs[3].psi], ps[0].dx ** 3)
+    assert rel_l2(sub["psik2"], want2["psik2"]) < 1e-12
+    driver.write_combined(str(tmp_path), "spherical-tophat", 3, got, 3, 16)
+    re = np.load(open(tmp_path / "spherical-tophat-combined" / "psik_00003_real", "rb"))
+    assert re.shape == (16, 16, 16, 1) and rel_l2(re[..., 0], want["psik"].real) < 1e-12
+    q = np.load(open(tmp_path / "spherical-tophat-combined" / "Qx_00003_real", "rb"))
+    assert q.shape == (1, 1, 1, 1)
+    sim.close()

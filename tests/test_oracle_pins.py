@@ -208,3 +208,18 @@ def test_get_tau_eds_known_answer():
     a = (a0 ** 1.5 + 1.5 * H0 * t) ** (2.0 / 3.0)
     expect = math.sqrt(1.5) * 2.0 * (a0 ** -0.5 - a ** -0.5)
     assert abs(o.get_tau(t, c) - expect) < 1e-8 * expect
+
+
+def test_synthesizer_combine_known_answers():
+    """synthesizer/src/main.rs:63-93,161-173: identical streams have Qx = 0; psik is the UN-normalised DFT
+    (psik[0] = sum psi); two streams psi and -psi average to zero with Qx = sum|psi|^2 dv."""
+    rng = np.random.default_rng(0)
+    psi = rng.standard_normal((8, 8, 8)) + 1j * rng.standard_normal((8, 8, 8))
+    dv = 0.3 ** 3
+    c = o.synthesizer_combine([psi, psi, psi], dv)
+    assert abs(c["Qx"]) < 1e-12 and np.allclose(c["psi"], psi)
+    assert abs(c["psik"][0, 0, 0] - psi.sum()) < 1e-10
+    assert abs(np.sum(c["psik2"]).real - 8 ** 3 * np.sum(np.abs(psi) ** 2)) < 1e-7     # Parseval, un-normalised
+    c = o.synthesizer_combine([psi, -psi], dv)
+    assert np.max(np.abs(c["psi"])) == 0.0
+    assert abs(c["Qx"] - np.sum(np.abs(psi) ** 2) * dv) < 1e-10
