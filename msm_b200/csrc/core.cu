@@ -352,6 +352,7 @@ struct msm_ctx {
     bool xl = true;   // contiguous-axis thread mapping (MSM_B200_XL=0 selects the generic mapping, for A/B timing)
     bool pipe = false; // persistent cp.async-pipelined kernel for N >= 128 (MSM_B200_PIPE=1; slower so far)
     bool fuse = true;  // fused passes (MSM_B200_FUSE=0 runs the plain 3+3 pass sequences, for A/B timing)
+    int l2_prefetch = 1;   // MSM_B200_PREFETCH=0 switches the L2 prefetch of the next item off (A/B timing)
     int tiles_per_cta = 4;   // consecutive tiles per CTA of the one-tile kernel; next item is prefetched into L2
     int num_sms = 148;
 };
@@ -555,6 +556,7 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         char nm[96];
         p.grid_ctas = ctx->num_sms;
         p.tiles_per_cta = pipe ? 1 : ctx->tiles_per_cta;
+        p.l2_prefetch = ctx->l2_prefetch;
         snprintf(nm, sizeof nm, "%s<%d,%s,%s,%s,%s>", pipe ? "fft_pipe" : "fft_pass", ctx->n, inv ? "inv" : "fwd",
                  lop_name(lop), sop_name(sop), axis == 0 ? "x" : axis == 1 ? "y" : "z");
         int rc;
@@ -757,6 +759,7 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     if (const char* e = getenv("MSM_B200_XL")) ctx->xl = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_PIPE")) ctx->pipe = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_FUSE")) ctx->fuse = atoi(e) != 0;
+    if (const char* e = getenv("MSM_B200_PREFETCH")) ctx->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
     ctx->lb = (cfg->dims == 3 && n >= 512) ? 4 : 0;
     if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;

@@ -86,6 +86,7 @@ struct PassParams {
     int grid_ctas;                        // persistent (pipelined) kernel: CTAs to launch = SM count
     int tiles_per_cta;                    // one-tile kernel: consecutive tiles walked by one CTA (L2 prefetch depth)
     int zero;                             // always 0; only the compiler does not know (see data_dependent)
+    int l2_prefetch;                      // pull the next item's tile into L2 while the current one computes
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
 
         // pull the NEXT item (partner stream of this tile, else first stream of the next tile) into L2 now, so its
         // loads find the data on chip: DRAM stays busy while this item computes
-        if (p.tiles_per_cta > 1 || p.gsz > 1) {
+        if (p.l2_prefetch && (p.tiles_per_cta > 1 || p.gsz > 1)) {
             const bool same_tile = !last_of_group;
             const int ntile = same_tile ? tile : tile + 1;
             const int nli = same_tile ? li + 1 : g * p.gsz;
