@@ -26,7 +26,7 @@
 #include "fft_pass.cuh"
 
 namespace msm {
-#define DECL(N) int launch_pass_##N(bool, int, int, bool, bool, const PassParams&, int, int, cudaStream_t);
+#define DECL(N) int launch_pass_##N(bool, int, int, bool, const PassParams&, int, int, cudaStream_t);
 DECL(2) DECL(4) DECL(8) DECL(16) DECL(32) DECL(64) DECL(128) DECL(256) DECL(512) DECL(1024)
 #undef DECL
 
@@ -350,7 +350,6 @@ struct msm_ctx {
     std::string err;
     pass_launcher_t launcher = nullptr;
     bool xl = true;   // contiguous-axis thread mapping (MSM_B200_XL=0 selects the generic mapping, for A/B timing)
-    bool pipe = false; // persistent cp.async-pipelined kernel for N >= 128 (MSM_B200_PIPE=1; slower so far)
     bool fuse = true;  // fused passes (MSM_B200_FUSE=0 runs the plain 3+3 pass sequences, for A/B timing)
     int l2_prefetch = 1;   // MSM_B200_PREFETCH=0 switches the L2 prefetch of the next item off (A/B timing)
     int tiles_per_cta = 4;   // consecutive tiles per CTA of the one-tile kernel; next item is prefetched into L2
@@ -533,8 +532,7 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
     for (size_t k = 0; k < seq.size(); ++k) {
         const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop;
         const bool inv = seq[k].inv;
-        const bool pipe = ctx->pipe && ctx->n >= PIPE_MIN_N;
-        const Geom g = make_geom(ctx, axis, pipe ? PIPE_T : (axis == 0 && ctx->xl) ? ctx->TX : ctx->T);
+        const Geom g = make_geom(ctx, axis, (axis == 0 && ctx->xl) ? ctx->TX : ctx->T);
         const bool first = (k == 0);
         p.src = first ? src : work;
         p.src_by_sid = first ? src_by_sid : work_by_sid;
@@ -554,15 +552,14 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         p.lvalid = g.lvalid;
         p.ntiles = g.ntiles;
         char nm[96];
-        p.grid_ctas = ctx->num_sms;
-        p.tiles_per_cta = pipe ? 1 : ctx->tiles_per_cta;
+        p.tiles_per_cta = ctx->tiles_per_cta;
         p.l2_prefetch = ctx->l2_prefetch;
-        snprintf(nm, sizeof nm, "%s<%d,%s,%s,%s,%s>", pipe ? "fft_pipe" : "fft_pass", ctx->n, inv ? "inv" : "fwd",
-                 lop_name(lop), sop_name(sop), axis == 0 ? "x" : axis == 1 ? "y" : "z");
+        snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s,%s>", ctx->n, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop),
+                 axis == 0 ? "x" : axis == 1 ? "y" : "z");
         int rc;
         {
             ProfScope ps(ctx, nm, pass_bytes(ctx, lop, sop, ns));
-            rc = ctx->launcher(inv, lop, sop, axis == 0 && ctx->xl, pipe, p, g.ntiles, groups, ctx->st);
+            rc = ctx->launcher(inv, lop, sop, axis == 0 && ctx->xl, p, g.ntiles, groups, ctx->st);
         }
         ctx->launches++;
         if (rc == -1) return fail(ctx, MSM_E_ARG, std::string("no kernel instance for ") + nm);
@@ -636,7 +633,7 @@ int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits, 
     o.poisson_coef = ctx->cfg.poisson_coeff / pow((double)ctx->n, (double)ctx->dims);
     o.maxbits = maxbits;
     const int d = ctx->dims;
-    const bool fuse = d >= 2 && ctx->fuse && !(ctx->pipe && ctx->n >= PIPE_MIN_N);
+    const bool fuse = d >= 2 && ctx->fuse;
     std::vector<PassSpec> seq;
     for (int a = x_fwd_done ? 1 : 0; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_NONE});
     if (fuse) {
@@ -651,8 +648,7 @@ int poisson(msm_ctx* ctx, int nbuf, bool max_only, unsigned long long* maxbits, 
 }
 
 bool full_fusion(const msm_ctx* ctx) {
-    return ctx->fuse && ctx->dims >= 2 && ctx->cfg.coupling == MSM_COUPLING_INDEPENDENT &&
-           !(ctx->pipe && ctx->n >= PIPE_MIN_N);
+    return ctx->fuse && ctx->dims >= 2 && ctx->cfg.coupling == MSM_COUPLING_INDEPENDENT;
 }
 
 // dt-potential of a chunk whose psi_k has ALREADY been taken through the inverse pass of the last axis into the
@@ -757,7 +753,6 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     for (int d = 0; d < cfg->dims; ++d) ctx->C *= n;
     ctx->launcher = get_pass_launcher(n);
     if (const char* e = getenv("MSM_B200_XL")) ctx->xl = atoi(e) != 0;
-    if (const char* e = getenv("MSM_B200_PIPE")) ctx->pipe = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_FUSE")) ctx->fuse = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_PREFETCH")) ctx->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
@@ -814,10 +809,9 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     CUC(cudaMalloc(&ctx->tw, sizeof(double2) * n));
     CUC(cudaMalloc(&ctx->dtab, sizeof(double2) * n * ctx->S));
     CUC(cudaMalloc(&ctx->ksq, sizeof(double) * n));
-    const Geom glast = make_geom(ctx, ctx->dims - 1, std::min(ctx->T, PIPE_T));   // finest tiling any kernel uses
+    const Geom glast = make_geom(ctx, ctx->dims - 1, std::min(ctx->T, 4));   // finest tiling any kernel uses
     ctx->ntiles_last = glast.ntiles;
-    ctx->ntiles_used = make_geom(ctx, ctx->dims - 1, (ctx->pipe && n >= PIPE_MIN_N) ? PIPE_T
-                                                     : (ctx->dims == 1 && ctx->xl) ? ctx->TX : ctx->T).ntiles;
+    ctx->ntiles_used = make_geom(ctx, ctx->dims - 1, (ctx->dims == 1 && ctx->xl) ? ctx->TX : ctx->T).ntiles;
     CUC(cudaMalloc(&ctx->alias_partial, sizeof(double) * (size_t)ctx->S * glast.ntiles));
     CUC(cudaMalloc(&ctx->alias_out, sizeof(double) * ctx->S));
     CUC(cudaMalloc(&ctx->maxbits, sizeof(unsigned long long) * (ctx->S + 2)));
@@ -1198,12 +1192,9 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
                 o.kick = kk;
                 o.dst2 = ctx->Tscr;
                 std::vector<PassSpec> seq;
-                if (d == 1) seq.push_back(PassSpec{0, false, L_KICK_IX, S_DRIFT_ALIAS_IZ});
-                else {
-                    seq.push_back(PassSpec{0, false, L_KICK_IX, S_DRIFT});
-                    for (int a = 1; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_DRIFT});
-                    seq.push_back(PassSpec{d - 1, false, L_NONE, S_DRIFT_ALIAS_IZ});
-                }
+                seq.push_back(PassSpec{0, false, L_KICK_IX, S_DRIFT});
+                for (int a = 1; a < d - 1; ++a) seq.push_back(PassSpec{a, false, L_NONE, S_DRIFT});
+                seq.push_back(PassSpec{d - 1, false, L_NONE, S_DRIFT_ALIAS_IZ});
                 if ((rc = run_passes(ctx, seq, cid, ns, ctx->X, 1, ctx->X, 1, o))) return rc;
             }
             // potential of the NEW psi_k (the reference computes it at the start of the next update(), :497)

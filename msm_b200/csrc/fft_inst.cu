@@ -1,5 +1,5 @@
 // fft_inst.cu -- instantiates the pass kernels for ONE transform length (compile with -DMSM_FFT_N=<N>).
-#include "fft_pipe.cuh"
+#include "fft_pass.cuh"
 
 #ifndef MSM_FFT_N
 #error "compile with -DMSM_FFT_N=<power of two>"
@@ -31,35 +31,14 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
     return (int)cudaPeekAtLastError();
 }
 
-template <bool INV, int LOP, int SOP, bool XL>
-int launch_pipe(const PassParams& p, cudaStream_t st) {
-    if constexpr (N >= PIPE_MIN_N) {
-        using PP = PipePlan<N>;
-        static bool configured = false;
-        constexpr int G = PP::groups(LOP == L_KICK);
-        const size_t smem = pipe_smem_bytes<N, LOP>();
-        auto kern = fft_pipe_kernel<N, INV, LOP, SOP, XL>;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            configured = true;
-        }
-        kern<<<p.grid_ctas, G * PP::GT, smem, st>>>(p);
-        return (int)cudaPeekAtLastError();
-    } else {
-        return -1;
-    }
-}
 }  // namespace
 
 // the (direction, load, store) combinations the step actually uses
-int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, bool pipe, const PassParams& p, int ntiles,
-                                     int groups, cudaStream_t st) {
-#define CASE(I, L, S)                                                                                          \
-    if (inv == I && lop == L && sop == S) {                                                                    \
-        if (pipe) return xl ? launch_pipe<I, L, S, true>(p, st) : launch_pipe<I, L, S, false>(p, st);          \
-        return xl ? launch<I, L, S, true>(p, ntiles, groups, st) : launch<I, L, S, false>(p, ntiles, groups, st); \
-    }
+int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, const PassParams& p, int ntiles, int groups,
+                                     cudaStream_t st) {
+#define CASE(I, L, S)                     \
+    if (inv == I && lop == L && sop == S) \
+        return xl ? launch<I, L, S, true>(p, ntiles, groups, st) : launch<I, L, S, false>(p, ntiles, groups, st);
     // inverse transforms
     CASE(true, L_NONE, S_NONE)
     CASE(true, L_NONE, S_SCALE)
@@ -80,7 +59,6 @@ int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, bool p
     CASE(false, L_KICK, S_DRIFT)
     CASE(false, L_KICK, S_DRIFT_ALIAS)
     CASE(false, L_KICK_IX, S_DRIFT)
-    CASE(false, L_KICK_IX, S_DRIFT_ALIAS_IZ)
     CASE(false, L_NONE, S_DRIFT_ALIAS_IZ)
 #undef CASE
     return -1;

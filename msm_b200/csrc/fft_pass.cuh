@@ -83,7 +83,6 @@ struct PassParams {
     double* alias_partial;                // [n_streams][ntiles] by stream id
     int ntiles;
     unsigned long long* maxbits;          // [2 * buffers]: bit patterns of non-negative doubles
-    int grid_ctas;                        // persistent (pipelined) kernel: CTAs to launch = SM count
     int tiles_per_cta;                    // one-tile kernel: consecutive tiles walked by one CTA (L2 prefetch depth)
     int zero;                             // always 0; only the compiler does not know (see data_dependent)
     int l2_prefetch;                      // pull the next item's tile into L2 while the current one computes
@@ -729,10 +728,8 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
 }
 
 // host-side launcher, one translation unit per N (fft_inst.cu compiled with -DMSM_FFT_N=<N>)
-typedef int (*pass_launcher_t)(bool inv, int lop, int sop, bool xl, bool pipe, const PassParams& p, int ntiles,
-                               int groups, cudaStream_t st);
-constexpr int PIPE_MIN_N = 128;   // the pipelined kernel (fft_pipe.cuh) exists for N >= 128
-constexpr int PIPE_T = 4;         // lines per tile of the pipelined kernel
+typedef int (*pass_launcher_t)(bool inv, int lop, int sop, bool xl, const PassParams& p, int ntiles, int groups,
+                               cudaStream_t st);
 pass_launcher_t get_pass_launcher(int n);
 // radices of the plan for length n (host side, for building the twiddle tables); returns the number of stages
 int plan_radices(int n, int radices[4]);
