@@ -69,6 +69,28 @@ def get_workers() -> int:
     return _WORKERS
 
 
+_POOL = None
+_PAR_MIN = 1 << 20      # grids below 2^20 cells are evaluated in one piece (bit-identical to the plain expression)
+
+
+def _pmap(fn, *arrays):
+    """fn(*arrays) evaluated slab by slab (axis 0) on the worker threads -- NumPy releases the GIL inside ufuncs, so the
+    element-wise passes of the step use all host cores like the FFTs do.  Element-wise results are bit-identical."""
+    global _POOL
+    a0 = arrays[0]
+    if _WORKERS <= 1 or a0.size < _PAR_MIN or a0.shape[0] < 2:
+        return fn(*arrays)
+    from concurrent.futures import ThreadPoolExecutor
+    if _POOL is None or _POOL._max_workers != _WORKERS:
+        _POOL = ThreadPoolExecutor(max_workers=_WORKERS)
+    nchunk = min(a0.shape[0], 4 * _WORKERS)
+    bounds = np.linspace(0, a0.shape[0], nchunk + 1).astype(int)
+    parts = list(_POOL.map(lambda i: fn(*(a[bounds[i]:bounds[i + 1]] for a in arrays)), range(nchunk)))
+    if np.ndim(parts[0]) == 0:
+        return parts                      # per-slab scalars (reductions): the caller combines them
+    return np.concatenate(parts, axis=0)
+
+
 # --------------------------------------------------------------------------------------
 # FFT wrappers + spectral grid  (simulator/src/utils/fft.rs)
 # --------------------------------------------------------------------------------------
@@ -592,24 +614,31 @@ class SimulationObject:
 
     def calculate_density(self) -> None:
         """simulation_object.rs:1031-1063: phi <- A * real(psi conj(psi)) cast to complex."""
-        self.phi = (self.density_prefactor() * (self.psi * np.conj(self.psi)).real).astype(np.complex128)
+        A = self.density_prefactor()
+        self.phi = _pmap(lambda a: (A * (a * np.conj(a)).real).astype(np.complex128), self.psi)
 
     def calculate_potential(self) -> None:
         """simulation_object.rs:1066-1110: phi = Re F^-1[ c F[rho] / k^2 , k=0 -> 0 ]."""
         p = self.parameters
         self.calculate_density()                                                # :1069
         self.phi = forward(self.phi)                                            # :1071
-        with np.errstate(divide="ignore", invalid="ignore"):
-            self.phi = (complex(self.poisson_coeff(), 0.0) * self.phi) / p.spec_grid.astype(np.complex128)  # :1076-1095
-        self.phi[np.isnan(self.phi)] = 0.0                                      # :1098-1102 (0/0 at k = 0)
+        c = complex(self.poisson_coeff(), 0.0)
+
+        def solve(f, k2):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                out = (c * f) / k2.astype(np.complex128)                        # :1076-1095
+            out[np.isnan(out)] = 0.0                                            # :1098-1102 (0/0 at k = 0)
+            return out
+
+        self.phi = _pmap(solve, self.phi, p.spec_grid)
         self.phi = inverse(self.phi)                                            # :1105
-        self.phi = self.phi.real.astype(np.complex128)                          # :1109
+        self.phi = _pmap(lambda f: f.real.astype(np.complex128), self.phi)      # :1109
 
     # ---- time step -------------------------------------------------------------------
     def get_timestep(self) -> Tuple[bool, float]:
         """simulation_object.rs:878-934 (static) / :939-990 (expanding)."""
         p = self.parameters
-        potential_max = float(np.max(np.abs(self.phi)))                         # :905 / :954
+        potential_max = float(np.max(_pmap(lambda f: np.max(np.abs(f)), self.phi)))   # :905 / :954
         self.last_potential_max = potential_max
         time_to_next_dump = (float(p.current_dumps + 1) * p.final_sim_time / float(p.num_data_dumps)) - p.time
         if not p.expanding:
@@ -639,9 +668,13 @@ class SimulationObject:
     def check_alias(self) -> Optional[float]:
         """simulation_object.rs:1249-1293: p = sum_{k^2 > k2_cutoff k2_max} |psik|^2 dk^dims."""
         p = self.parameters
-        a = (self.psik * np.conj(self.psik)).real                               # :1259
-        mask = p.spec_grid > (p.k2_max * p.k2_cutoff)                           # :1262-1269
-        p_mass = float(np.sum(np.where(mask, a, 0.0))) * p.dk ** float(p.dims)  # :1270-1285
+        cut = p.k2_max * p.k2_cutoff
+
+        def masked_sum(pk, k2):
+            a = (pk * np.conj(pk)).real                                         # :1259
+            return np.sum(np.where(k2 > cut, a, 0.0))                           # :1262-1280
+
+        p_mass = float(np.sum(_pmap(masked_sum, self.psik, p.spec_grid))) * p.dk ** float(p.dims)   # :1281-1285
         self.last_alias_mass = p_mass
         return p_mass if p_mass > p.alias_threshold else None                   # :1288-1292
 
@@ -663,27 +696,27 @@ class SimulationObject:
         self.calculate_potential()                                              # :497 / :692
         dump, dt = self.get_timestep()                                          # :500 / :695
         self.last_dt = dt
-        if not p.expanding:
-            k_evolution = np.exp(complex(0.0, -dt / 4.0 * p.hbar_) * p.spec_grid.astype(np.complex128))  # :504-514
-        else:
-            k_evolution = np.exp(complex(0.0, -dt / 4.0) * p.spec_grid.astype(np.complex128))            # :699-706
-        self.psik = self.psik * k_evolution                                     # :516 / :708
+        kc = complex(0.0, -dt / 4.0 * p.hbar_) if not p.expanding else complex(0.0, -dt / 4.0)   # :504-514 / :699-706
+        k_evolution = _pmap(lambda k2: np.exp(kc * k2.astype(np.complex128)), p.spec_grid)
+        self.psik = _pmap(np.multiply, self.psik, k_evolution)                  # :516 / :708
         self.psi = inverse(self.psik)                                           # :523 / :715
         self.calculate_potential()                                              # :530 / :722
         if not p.expanding:
-            r_evolution = np.exp(complex(0.0, -dt / p.hbar_) * self.phi)        # :535-542
-            self.psi = self.psi * r_evolution                                   # :545
+            rc = complex(0.0, -dt / p.hbar_)
+            r_evolution = _pmap(lambda f: np.exp(rc * f), self.phi)             # :535-542
+            self.psi = _pmap(np.multiply, self.psi, r_evolution)                # :545
         else:
             for _ in range(2):                                                  # :726
                 a = self.scale_factor_solver.get_a()                            # :728
-                r_evolution = np.exp(complex(0.0, -dt / 2.0 * a) * self.phi)    # :729-739
-                self.psi = self.psi * r_evolution                               # :742
+                rc = complex(0.0, -dt / 2.0 * a)
+                r_evolution = _pmap(lambda f: np.exp(rc * f), self.phi)         # :729-739
+                self.psi = _pmap(np.multiply, self.psi, r_evolution)            # :742
                 dt_half = self.calculate_dt_from_dtau(dt / 2.0)                 # :751-752
                 self.scale_factor_solver.step(dt_half)                          # :755-756
                 p.time = p.time + dt_half                                       # :757
                 p.tau = p.tau + dt / 2.0                                        # :759
         self.psik = forward(self.psi)                                           # :552 / :761
-        self.psik = self.psik * k_evolution                                     # :562-574 / :771-780 (same array values)
+        self.psik = _pmap(np.multiply, self.psik, k_evolution)                  # :562-574 / :771-780 (same array values)
         self.psi = inverse(self.psik)                                           # :581 / :787
         if not p.expanding:
             p.time = p.time + dt                                                # :590
