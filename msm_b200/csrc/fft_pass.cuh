@@ -290,6 +290,17 @@ template <int N, bool XL> __device__ __forceinline__ int sm_index(int pos, int l
     return pos * tile_T<N, false>() + l;
 }
 
+// Exchange barrier.  Contiguous-axis mapping with NT a multiple of 32: the NT threads of one line are whole warps and
+// exchange only among themselves, so each line gets its own named barrier (1 + l) and never waits for the other lines
+// of the tile.  Otherwise the lines are interleaved across all warps: CTA-wide barrier.
+template <int N, bool XL> __device__ __forceinline__ void exchange_barrier(int l) {
+    if constexpr (XL && (Plan<N>::NT % 32 == 0)) {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + l), "n"(Plan<N>::NT) : "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
 template <int N, bool INV, bool XL, int Q>
 __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm, int t, int l,
                                            const double2* __restrict__ tw) {
@@ -318,7 +329,7 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
                 sm[sm_index<N, XL>((kappa + L * k) * M + nu, l)] = x;
             }
         }
-        __syncthreads();
+        exchange_barrier<N, XL>(l);
         constexpr int R2 = PL::R[Q + 1];
         constexpr int L2 = L * R;
         constexpr int M2 = N / (L2 * R2);
@@ -330,7 +341,7 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
 #pragma unroll
             for (int n = 0; n < R2; ++n) v[c * R2 + n] = sm[sm_index<N, XL>(kappa * (M2 * R2) + n * M2 + nu, l)];
         }
-        __syncthreads();
+        exchange_barrier<N, XL>(l);
         run_stages<N, INV, XL, Q + 1>(v, sm, t, l, tw);
     }
 }
@@ -504,6 +515,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
                 }
                 run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
                 outputs_to_inputs<N>(v);
+                __syncthreads();   // phi_a slots span the whole exchange buffer: all lines must be done with it
                 double* phia = reinterpret_cast<double*>(sm);
 #pragma unroll
                 for (int i = 0; i < E; ++i) {
