@@ -114,11 +114,11 @@ MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #undef MSM_PLAN
 
 // Tile height.  Strided axes need T = 8 lines (full 128-byte rows); on the contiguous axis lines are 16*N contiguous
-// bytes anyway, so large transforms use T = 4: half the shared memory and threads per CTA, twice the CTAs per SM --
-// the load / compute / store phases of four CTAs interleave better than those of two (matters most for the fused
+// bytes anyway, so large transforms use T = 2 (measured: 4 -> +3 %, 2 -> +1 % more): a quarter of the shared memory and threads per CTA, 8 CTAs per SM --
+// the load / compute / store phases of eight small CTAs interleave better than those of two big ones (matters most for the fused
 // two-transform kernels, all of which run on the contiguous axis or tolerate it).
 #ifndef MSM_TX
-#define MSM_TX 4
+#define MSM_TX 2
 #endif
 template <int N, bool XL> constexpr int tile_T() { return (XL && N >= 256 && Plan<N>::T == 8) ? MSM_TX : Plan<N>::T; }
 template <int N, bool XL> constexpr int tile_threads() { return Plan<N>::NT * tile_T<N, XL>(); }
