@@ -308,8 +308,8 @@ def main():
             check(lib.msm_sim_set_psi(sim.handle, s, hnp.ctypes.data_as(dp)), sim.handle, sim=True)
         for _ in range(args.steps):
             sim.update()
-        for s in range(n_local):                                   # one dump: D2H of every stream, re/im planes
-            check(lib.msm_sim_get_psi(sim.handle, s, renp.ctypes.data_as(dp), imnp.ctypes.data_as(dp)), sim.handle, sim=True)
+        # one dump: D2H of every stream as re/im planes, transform of stream i+1 overlapped with the copy of stream i
+        g.get_psi_many(list(range(n_local)), [renp] * n_local, [imnp] * n_local)
         sec = time.perf_counter() - t0
         barrier()
         sec = max_over_ranks(sec)
@@ -318,7 +318,7 @@ def main():
                "h2d_bytes_per_step": int(16 * cells * n_local / args.steps + tab + 16 * n_local),
                "d2h_bytes_per_step": int(16 * cells * n_local / args.steps + 16 * n_local),
                "seconds": sec, "what": "msm_sim_set_psi of all streams from pinned host memory + K x msm_sim_update "
-               "+ msm_sim_get_psi of all streams (one dump) inside the timed region"}
+               "+ msm_get_psi_many of all streams (one dump) inside the timed region"}
     sim.close()
 
     # ---- the reference's CPU algorithm beside it (rank 0, N = 1 only) ------------------------------------------

@@ -107,6 +107,10 @@ int msm_set_psi_planes(msm_ctx* ctx, int32_t stream, const double* re, const dou
  * utils/io.rs:46-47,58-60,72-74).  Either plane pointer may be NULL. */
 int msm_get_psi(msm_ctx* ctx, int32_t stream, double* re, double* im);
 int msm_get_psi_interleaved(msm_ctx* ctx, int32_t stream, double* out /* 2*n^dims */);
+/* Dump of several streams: the inverse transform and plane split of stream i+1 run on the compute
+ * stream while the planes of stream i cross PCIe on a copy stream (two staging buffers).  re[i] / im[i] receive stream
+ * streams[i]; use pinned host memory for real overlap.  The reference copies synchronously (utils/io.rs:46-47). */
+int msm_get_psi_many(msm_ctx* ctx, int32_t n, const int32_t* streams, double* const* re, double* const* im);
 /* psi_k as the reference holds it after `update()` (second drift applied, :574). */
 int msm_get_psik_interleaved(msm_ctx* ctx, int32_t stream, double* out /* 2*n^dims */);
 
@@ -148,6 +152,10 @@ int msm_spec_grid(int32_t device, int32_t dims, int32_t size, double dx, double*
 int msm_ic_cold_gauss(msm_ctx* ctx, int32_t stream, const double* mean, const double* std);
 int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t stream, double axis_length, double radius, double delta,
                             double slope);
+/* cold_gauss_kspace (ics.rs:282-431): Gaussian in k with uniform random phases exp(2 pi i u), then the forward transform.
+ * The phases come from the same counter-based Philox as the sampler (draw slot 7); only dims == 3 is meaningful in the
+ * reference (it hard-codes a 3-D phase array, ics.rs:401-406). */
+int msm_ic_cold_gauss_kspace(msm_ctx* ctx, int32_t stream, const double* mean, const double* std, uint64_t phase_seed);
 int msm_ic_copy(msm_ctx* ctx, int32_t dst_stream, int32_t src_stream);
 int msm_sample_perturbation(msm_ctx* ctx, int32_t stream, int32_t scheme, uint64_t seed, double n_tot);
 

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "msm_set_psi_planes": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_get_psi": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_get_psi_interleaved": (C.c_int, [_vp, C.c_int32, _dp]),
+    "msm_get_psi_many": (C.c_int, [_vp, C.c_int32, _ip, C.POINTER(_dp), C.POINTER(_dp)]),
     "msm_get_psik_interleaved": (C.c_int, [_vp, C.c_int32, _dp]),
     "msm_potential_max": (C.c_int, [_vp, _ip, _dp]),
     "msm_get_potential": (C.c_int, [_vp, C.c_int32, _dp]),
@@ -91,6 +92,7 @@ PROTOTYPES = {
     "msm_spec_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp]),
     "msm_ic_cold_gauss": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_ic_spherical_tophat": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "msm_ic_cold_gauss_kspace": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.c_uint64]),
     "msm_ic_copy": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "msm_sample_perturbation": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_double]),
     "msm_ensemble_accumulate": (C.c_int, [_vp, _ip]),

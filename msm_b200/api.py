@@ -137,6 +137,15 @@ class Context:
         self._chk(lib.msm_get_psi(self.handle, stream, _f64(re.reshape(-1)), _f64(im.reshape(-1))))
         return re, im
 
+    def get_psi_many(self, streams: Sequence[int], re: Sequence[np.ndarray], im: Sequence[np.ndarray]) -> None:
+        """Pipelined dump (row f-2): planes of stream i cross PCIe while stream i+1 is transformed.  `re[i]`, `im[i]`
+        are float64 arrays of n^dims elements (pinned memory gives real overlap); the same array may be passed twice."""
+        n = len(streams)
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+        rp = (_dp * n)(*[_f64(a.reshape(-1)) for a in re])
+        ip = (_dp * n)(*[_f64(a.reshape(-1)) for a in im])
+        self._chk(lib.msm_get_psi_many(self.handle, n, ids.ctypes.data_as(_ip), rp, ip))
+
     def get_psik(self, stream: int) -> np.ndarray:
         out = np.empty(self.shape, dtype=np.complex128)
         self._chk(lib.msm_get_psik_interleaved(self.handle, stream, _f64(out.reshape(-1).view(np.float64))))
@@ -190,6 +199,12 @@ class Context:
 
     def ic_spherical_tophat(self, stream: int, axis_length: float, radius: float, delta: float, slope: float) -> None:
         self._chk(lib.msm_ic_spherical_tophat(self.handle, stream, axis_length, radius, delta, slope))
+
+    def ic_cold_gauss_kspace(self, stream: int, mean: Sequence[float], std: Sequence[float], phase_seed: int = 0) -> None:
+        m = np.ascontiguousarray(mean, dtype=np.float64)
+        s = np.ascontiguousarray(std, dtype=np.float64)
+        assert m.size == self.dims and s.size == self.dims
+        self._chk(lib.msm_ic_cold_gauss_kspace(self.handle, stream, _f64(m), _f64(s), int(phase_seed)))
 
     def ic_copy(self, dst: int, src: int) -> None:
         self._chk(lib.msm_ic_copy(self.handle, dst, src))

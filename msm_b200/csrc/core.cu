@@ -250,6 +250,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
 }
+// psi *= exp(2 pi i u(q)), u from Philox draw slot `draw` (cold_gauss_kspace random phases, ics.rs:407-423)
+__global__ void k_random_phase(double2* __restrict__ psi, long long cells, uint64_t seed, uint32_t draw, int n, int lb) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x) {
+        uint32_t c0 = (uint32_t)q, c1 = (uint32_t)((uint64_t)q >> 32), c2 = draw, c3 = 0u;
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+        double sn, cs;
+        sincos(2.0 * 3.14159265358979323846 * u53(c0, c1), &sn, &cs);
+        const long long b = blk_index(q, n, lb);
+        const double2 v = psi[b];
+        psi[b] = make_double2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+    }
+}
 // sample_quantum_perturbation, Wigner / Husimi (ics.rs:560-646): psi = (psi sqrt(dV) + (N + iN) / div) / sqrt(dV)
 __global__ void k_sample_gauss(double2* __restrict__ psi, long long cells, uint64_t seed, double sqrt_dv, double div,
                                int n, int lb) {
@@ -341,6 +353,8 @@ struct msm_ctx {
     uint64_t bytes = 0, launches = 0;
     void* comm = nullptr;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;
+    cudaStream_t copy_st = nullptr;                       // msm_get_psi_many: D2H overlapped with compute
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // profiling
     bool prof = false;
     std::vector<ProfEvent> prof_pending;
@@ -882,6 +896,11 @@ void msm_destroy(msm_ctx* ctx) {
     if (ctx->h_dtab) cudaFreeHost(ctx->h_dtab);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->dtab_done) cudaEventDestroy(ctx->dtab_done);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     if (ctx->tm_a) cudaEventDestroy(ctx->tm_a);
     if (ctx->tm_b) cudaEventDestroy(ctx->tm_b);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -936,7 +955,7 @@ int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* 
 }
 
 // psi of stream s into scratch slot 0 (or X itself when no transform has happened yet); returns the device pointer
-static int psi_on_device(msm_ctx* ctx, int s, const double2** out) {
+static int psi_on_device(msm_ctx* ctx, int s, const double2** out, int slot = 0) {
     if (!ctx->has_psi[s]) return fail(ctx, MSM_E_STATE, "stream has no wavefunction");
     if (!ctx->in_k[s]) {
         *out = ctx->X + (size_t)s * ctx->C;
@@ -948,9 +967,10 @@ static int psi_on_device(msm_ctx* ctx, int s, const double2** out) {
     o.scale = 1.0 / sqrt((double)ctx->n);
     int id = s;
     // first pass reads X[s], every pass writes scratch slot 0 (work is indexed by local index)
-    int rc = run_transform(ctx, true, &id, 1, ctx->X, 1, ctx->Tscr, 0, o);
+    double2* work = ctx->Tscr + (size_t)slot * ctx->C;
+    int rc = run_transform(ctx, true, &id, 1, ctx->X, 1, work, 0, o);
     if (rc) return rc;
-    *out = ctx->Tscr;
+    *out = work;
     return MSM_OK;
 }
 
@@ -983,6 +1003,48 @@ int msm_get_psi(msm_ctx* ctx, int32_t s, double* re, double* im) {
     CU(cudaGetLastError());
     if (re) CU(cudaMemcpyAsync(re, planes, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
     if (im) CU(cudaMemcpyAsync(im, planes + ctx->C, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+int msm_get_psi_many(msm_ctx* ctx, int32_t n, const int32_t* streams, double* const* re, double* const* im) {
+    if (!ctx || n < 0 || (n > 0 && (!streams || !re || !im))) return fail(ctx, MSM_E_ARG, "msm_get_psi_many: bad argument");
+    for (int i = 0; i < n; ++i)
+        if (streams[i] < 0 || streams[i] >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_get_psi_many: stream out of range");
+    const int npair = (ctx->chunk + 1) / 2;
+    if (npair < 2 || ctx->chunk < 2) {   // not enough staging for a pipeline: one stream after the other
+        for (int i = 0; i < n; ++i) {
+            int rc = msm_get_psi(ctx, streams[i], re[i], im[i]);
+            if (rc) return rc;
+        }
+        return MSM_OK;
+    }
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->copy_st) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t pb = sizeof(double) * (size_t)ctx->C;
+    for (int i = 0; i < n; ++i) {
+        const int b = i & 1;
+        if (i >= 2) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copied[b], 0));   // staging b has left the device
+        const double2* d = nullptr;
+        int rc = psi_on_device(ctx, streams[i], &d, b);
+        if (rc) return rc;
+        double* planes = reinterpret_cast<double*>(ctx->P + (size_t)b * ctx->C);
+        k_deinterleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, planes, planes + ctx->C, ctx->C, ctx->n, ctx->lb);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_ready[b], ctx->st));
+        CU(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_ready[b], 0));
+        if (re[i]) CU(cudaMemcpyAsync(re[i], planes, pb, cudaMemcpyDeviceToHost, ctx->copy_st));
+        if (im[i]) CU(cudaMemcpyAsync(im[i], planes + ctx->C, pb, cudaMemcpyDeviceToHost, ctx->copy_st));
+        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_st));
+    }
+    CU(cudaStreamSynchronize(ctx->copy_st));
     CU(cudaStreamSynchronize(ctx->st));
     return MSM_OK;
 }
@@ -1353,6 +1415,48 @@ int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double*
     int rc = normalize_on_device(ctx, psi);   // ics.rs:142
     if (rc) return rc;
     ctx->in_k[s] = 0;
+    ctx->has_psi[s] = 1;
+    ctx->pmax_valid[s] = 0;
+    return MSM_OK;
+}
+
+int msm_ic_cold_gauss_kspace(msm_ctx* ctx, int32_t s, const double* mean, const double* std, uint64_t phase_seed) {
+    if (!ctx || !mean || !std || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_cold_gauss_kspace: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int n = ctx->n, d = ctx->dims;
+    const double dk = ctx->cfg.dx;   // dk = dx in the reference (simulation_object.rs:263)
+    if (3 * n > 4096) return fail(ctx, MSM_E_ARG, "size too large for the IC staging buffer");
+    std::vector<double> g(3 * n, 1.0);
+    for (int a = 0; a < d; ++a) {   // 1-D factors on the k grid, each normalised with dk^dims (ics.rs:336-390)
+        double norm = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double k = ((i < n / 2) ? (double)i : (double)(i - n)) / ((double)n * ctx->cfg.dx);
+            const double v = exp(-0.5 * pow((k - mean[a]) / std[a], 2.0));
+            g[a * n + i] = v;
+            norm += v * v;
+        }
+        const double f = sqrt(pow(dk, -(double)d) / norm);
+        for (int i = 0; i < n; ++i) g[a * n + i] *= f;
+    }
+    CU(cudaMemcpyAsync(ctx->scratch_small, g.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->st));
+    double2* psi = ctx->X + (size_t)s * ctx->C;
+    k_ic_separable<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->scratch_small, n, d, 1.0, ctx->lb);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->st));
+    int rc = normalize_on_device(ctx, psi);   // ics.rs:395
+    if (rc) return rc;
+    k_random_phase<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->C, phase_seed, 7u, n, ctx->lb);   // ics.rs:407-423
+    ctx->launches++;
+    CU(cudaGetLastError());
+    XformOps o;   // forward_inplace (ics.rs:425), unitary
+    o.gsz = 1;
+    o.sop_each = o.sop_last = S_SCALE;
+    o.scale = 1.0 / sqrt((double)n);
+    int id = s;
+    rc = run_transform(ctx, false, &id, 1, ctx->X, 1, ctx->X, 1, o);
+    if (rc) return rc;
+    ctx->in_k[s] = 0;   // what X holds now is the reference's spatial psi
     ctx->has_psi[s] = 1;
     ctx->pmax_valid[s] = 0;
     return MSM_OK;

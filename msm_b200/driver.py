@@ -39,6 +39,9 @@ def load_initial_conditions(sim: SimulationObject, cfg: RunConfig, local: List[i
                 g.set_psi_planes(0, re_, im_)
             elif kind == "ColdGauss":                                # ics.rs:24-162
                 g.ic_cold_gauss(0, [float(v) for v in ics["mean"]], [float(v) for v in ics["std"]])
+            elif kind == "ColdGaussKSpace":                          # ics.rs:282-431
+                g.ic_cold_gauss_kspace(0, [float(v) for v in ics["mean"]], [float(v) for v in ics["std"]],
+                                       int(ics.get("phase_seed") or 0))
             elif kind == "SphericalTophat":                          # ics.rs:165-280
                 g.ic_spherical_tophat(0, p.axis_length, float(ics["radius"]), float(ics["delta"]), float(ics["slope"]))
             else:

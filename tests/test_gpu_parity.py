@@ -127,6 +127,14 @@ def test_single_step_fields_match_oracle():
         assert rel_l2(ctx.get_psi(i), s.psi) < 1e-12
         re, im = ctx.get_psi_planes(i)
         assert np.array_equal(re + 1j * im, ctx.get_psi(i))
+    # pipelined dump of several streams (row f-2), in a scrambled order
+    order = [2, 0, 3, 1, 2]
+    res = [np.empty((16,) * 3) for _ in order]
+    ims = [np.empty((16,) * 3) for _ in order]
+    ctx.get_psi_many(order, res, ims)
+    for j, i in enumerate(order):
+        assert np.array_equal(res[j] + 1j * ims[j], ctx.get_psi(i))
+    for i, s in enumerate(sims):
         assert alias_close(alias[i], s.last_alias_mass)
     ctx.close()
 
@@ -352,6 +360,10 @@ def test_device_initial_conditions_match_oracle():
     ctx = make_ctx(g, 1)
     ctx.ic_cold_gauss(0, [15.0] * 3, [10.0] * 3)
     assert rel_l2(ctx.get_psi(0), o.cold_gauss([15.0] * 3, [10.0] * 3, g)) < 1e-13
+    # cold_gauss_kspace (ics.rs:282-431): Gaussian in k, random phases, forward transform
+    ctx.ic_cold_gauss_kspace(0, [0.1, 0.0, -0.1], [0.3, 0.25, 0.2], phase_seed=5)
+    want = o.cold_gauss_kspace([0.1, 0.0, -0.1], [0.3, 0.25, 0.2], g, 5)
+    assert rel_l2(ctx.get_psi(0), want) < 1e-13 and o.check_norm(want, g.dx, 3)
     ctx.close()
 
 
