@@ -80,6 +80,41 @@ def run(cfg: RunConfig, out_root: str = "sim-data", rank: int = 0, nranks: int =
     return {"streams": len(local), "stream_steps": steps, "seconds": wall}
 
 
+def export_params(cfg: RunConfig, path: str, base_dir: str = ".") -> None:
+    """Write the resolved scalars of a reference TOML as the `key = value` file the native host
+    (`msm_b200/msm-simulator-b200 --params`, csrc/msm_simulator.cpp) reads."""
+    p = cfg.parameters
+    lines = [f"sim_name = {cfg.sim_name}", f"dims = {p.dims}", f"size = {p.size}", f"axis_length = {p.axis_length!r}",
+             f"time = {p.time!r}", f"final_sim_time = {p.final_sim_time!r}", f"cfl = {p.cfl!r}",
+             f"num_data_dumps = {p.num_data_dumps}", f"total_mass = {p.total_mass!r}",
+             f"particle_mass = {p.particle_mass!r}", f"hbar_ = {p.hbar_!r}", f"k2_cutoff = {p.k2_cutoff!r}",
+             f"alias_threshold = {p.alias_threshold!r}"]
+    c = p.cosmology
+    if c is not None:
+        lines += ["expanding = 1", f"omega_matter_now = {c.omega_matter_now!r}",
+                  f"omega_radiation_now = {c.omega_radiation_now!r}", f"h = {c.h!r}", f"z0 = {c.z0!r}"]
+        if c.max_dloga is not None:
+            lines.append(f"max_dloga = {c.max_dloga!r}")
+    ics = cfg.ics
+    if ics["type"] == "ColdGauss":
+        lines.append("ics = ColdGauss " + " ".join(repr(float(v)) for v in list(ics["mean"]) + list(ics["std"])))
+    elif ics["type"] == "SphericalTophat":
+        lines.append(f"ics = SphericalTophat {float(ics['radius'])!r} {float(ics['delta'])!r} {float(ics['slope'])!r}")
+    elif ics["type"] == "UserSpecified":
+        z = np.load(os.path.join(base_dir, ics["path"]))
+        raw = path + ".ic.f64"
+        (np.asarray(z["real"], np.float64) + 1j * np.asarray(z["imag"], np.float64)).astype(np.complex128).tofile(raw)
+        lines.append(f"ics = File {raw}")
+    else:
+        raise NotImplementedError(ics["type"])
+    seeds = [s.seed for s in cfg.streams if s.seed is not None]
+    if seeds:
+        lines.append("seeds = " + ",".join(str(s) for s in seeds))
+        lines.append(f"scheme = {cfg.streams[0].scheme}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(prog="msm_b200", description="B200-native msm-simulator time-evolution loop")
     ap.add_argument("--toml", "-t", required=True)
@@ -87,8 +122,14 @@ def main(argv=None) -> int:
     ap.add_argument("--test", action="store_true", help="construct the streams and exit (main.rs:59)")
     ap.add_argument("--out", default="sim-data")
     ap.add_argument("--static", action="store_true", help="ignore [cosmology] (cargo feature `expanding` off)")
+    ap.add_argument("--export-params", metavar="FILE",
+                    help="write the resolved parameters for the native host (msm-simulator-b200 --params FILE) and exit")
     args = ap.parse_args(argv)
     cfg = read_toml(args.toml, expanding=False if args.static else None)
+    if args.export_params:
+        tdir = os.path.dirname(os.path.abspath(args.toml))
+        export_params(cfg, args.export_params, "." if os.path.exists(cfg.ics.get("path", "")) else os.path.dirname(tdir))
+        return 0
     rank = int(os.environ.get("RANK", "0"))
     nranks = int(os.environ.get("WORLD_SIZE", "1"))
     device = int(os.environ.get("LOCAL_RANK", "0"))

@@ -89,3 +89,12 @@ def test_product_never_imports_the_oracle():
     bench = open(os.path.join(ROOT, "bench.py")).read()
     # bench.py may touch the oracle only inside the two CPU-baseline functions
     assert bench.count("from oracle import") == 3
+
+
+def test_native_host_binary_is_built_and_links_only_the_c_abi():
+    exe = os.path.join(ROOT, "msm_b200", "msm-simulator-b200")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr
+    needed = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libmsm_b200.so" in needed and "torch" not in needed and "python" not in needed

@@ -492,3 +492,50 @@ def test_ensemble_statistics_match_synthesizer_restatement(monkeypatch, tmp_path
     q = np.load(open(tmp_path / "spherical-tophat-combined" / "Qx_00003_real", "rb"))
     assert q.shape == (1, 1, 1, 1)
     sim.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the native (C++) host over the C ABI: msm_b200/msm-simulator-b200, mirror of simulator/src/main.rs
+# ---------------------------------------------------------------------------------------------------------------
+def test_native_host_runs_a_reference_config(tmp_path):
+    import subprocess
+    from msm_b200 import driver
+    from msm_b200.config import read_toml
+    from conftest import ROOT
+    toml = tmp_path / "run.toml"
+    toml.write_text("""
+axis_length = 30
+final_sim_time = 0.8
+cfl = 0.5
+num_data_dumps = 4
+total_mass = 1e11
+hbar_ = 0.05
+sim_name = "tophat-native"
+k2_cutoff = 0.95
+alias_threshold = 0.02
+dims = 3
+size = 16
+[ics]
+type = "SphericalTophat"
+radius = 5.0
+slope = 50
+delta = 100
+[sampling]
+seeds = "3 to 4"
+scheme = "Wigner"
+""")
+    cfg = read_toml(str(toml))
+    params = tmp_path / "run.params"
+    driver.export_params(cfg, str(params))
+    exe = os.path.join(ROOT, "msm_b200", "msm-simulator-b200")
+    out = subprocess.run([exe, "--params", str(params), "--out", str(tmp_path / "sim-data"), "--verbose"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "3 streams" in out.stdout
+    for p in o.simulation_iter(o.read_toml(str(toml))):
+        ref = o.run_stream(p, o.initial_wavefunction(p))
+        assert len(ref.dumps) == 5
+        for idx, psi in ref.dumps:
+            d = tmp_path / "sim-data" / p.sim_name
+            got = np.load(open(d / f"psi_{idx:05d}_real", "rb"))[..., 0] + 1j * np.load(open(d / f"psi_{idx:05d}_imag", "rb"))[..., 0]
+            assert rel_l2(got, psi) < 1e-10, (p.sim_name, idx)
