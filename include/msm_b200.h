@@ -111,6 +111,17 @@ int msm_get_psi_interleaved(msm_ctx* ctx, int32_t stream, double* out /* 2*n^dim
  * stream while the planes of stream i cross PCIe on a copy stream (two staging buffers).  re[i] / im[i] receive stream
  * streams[i]; use pinned host memory for real overlap.  The reference copies synchronously (utils/io.rs:46-47). */
 int msm_get_psi_many(msm_ctx* ctx, int32_t n, const int32_t* streams, double* const* re, double* const* im);
+/* Asynchronous transfers: the same upload / download as msm_set_psi / msm_get_psi, but the call only enqueues work --
+ * uploads on a dedicated stream (the compute stream waits for a stream's upload the next time it touches that
+ * stream), downloads after everything already enqueued for that stream, through two dedicated staging buffers on
+ * a copy stream -- so that PCIe traffic of some streams overlaps the step kernels of others (the reference copies
+ * synchronously: `Array::new` ics.rs:726, `array.host` utils/io.rs:46-47).  EXCEPTION to the buffer convention above:
+ * the host buffers are retained until msm_transfers_wait returns (pinned memory is needed for real overlap).
+ * msm_chunk_streams returns the resolved streams-per-launch-group of the context. */
+int msm_upload_begin(msm_ctx* ctx, int32_t stream, const double* psi_interleaved);
+int msm_download_begin(msm_ctx* ctx, int32_t stream, double* re, double* im);
+int msm_transfers_wait(msm_ctx* ctx);
+int msm_chunk_streams(const msm_ctx* ctx, int32_t* chunk);
 /* psi_k as the reference holds it after `update()` (second drift applied, :574). */
 int msm_get_psik_interleaved(msm_ctx* ctx, int32_t stream, double* out /* 2*n^dims */);
 
@@ -249,6 +260,19 @@ int msm_sim_set_psi(msm_sim* sim, int32_t stream, const double* psi_interleaved)
 /* One `update()` (:475 / :669) for every stream that is not finished.  Returns MSM_E_ALIASING if any stream
  * crossed alias_threshold (its state says which); the other streams have still been advanced. */
 int msm_sim_update(msm_sim* sim);
+/* The same for a subset: subset[s] != 0 selects stream s (n_streams entries, NULL = all).  Independent coupling only. */
+int msm_sim_update_streams(msm_sim* sim, const int32_t* subset);
+/* The reference's outer loop over the streams of one TOML (simulator/src/main.rs:43-85): for stream streams[i],
+ * upload the initial wavefunction psi_in[i] (interleaved, 2*n^dims doubles; a fresh SimulationObject: time, dumps and
+ * scale factor restart.  NULL entry / NULL array = keep the stream's current state), `while not_finished() { update() }`
+ * (main.rs:65-69; at most max_updates calls per stream when max_updates > 0), then write the final psi as re / im planes
+ * to re_out[i] / im_out[i] (either may be NULL).  The reference runs its streams one after another; here they advance
+ * in groups, and the uploads of the next group and the downloads of the previous one overlap the step kernels of the
+ * current one (pinned host memory is needed for that overlap).  Host buffers are read / written until the call
+ * returns.  A stream that crosses alias_threshold stops there (the reference panics, :607-617) and the call returns
+ * MSM_E_ALIASING after finishing the others.  Independent coupling only. */
+int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const double* const* psi_in,
+                        double* const* re_out, double* const* im_out, uint64_t max_updates);
 int msm_sim_not_finished(const msm_sim* sim);                        /* 1 while any stream has time < final    */
 int msm_sim_state(const msm_sim* sim, int32_t stream, msm_stream_state* out);
 int msm_sim_get_psi(msm_sim* sim, int32_t stream, double* re, double* im);

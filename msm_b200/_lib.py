@@ -82,6 +82,10 @@ PROTOTYPES = {
     "msm_get_psi": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_get_psi_interleaved": (C.c_int, [_vp, C.c_int32, _dp]),
     "msm_get_psi_many": (C.c_int, [_vp, C.c_int32, _ip, C.POINTER(_dp), C.POINTER(_dp)]),
+    "msm_upload_begin": (C.c_int, [_vp, C.c_int32, _dp]),
+    "msm_download_begin": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
+    "msm_transfers_wait": (C.c_int, [_vp]),
+    "msm_chunk_streams": (C.c_int, [_vp, _ip]),
     "msm_get_psik_interleaved": (C.c_int, [_vp, C.c_int32, _dp]),
     "msm_potential_max": (C.c_int, [_vp, _ip, _dp]),
     "msm_get_potential": (C.c_int, [_vp, C.c_int32, _dp]),
@@ -109,6 +113,8 @@ PROTOTYPES = {
     "msm_sim_derived": (C.c_int, [_vp, C.POINTER(MsmDerived)]),
     "msm_sim_set_psi": (C.c_int, [_vp, C.c_int32, _dp]),
     "msm_sim_update": (C.c_int, [_vp]),
+    "msm_sim_update_streams": (C.c_int, [_vp, _ip]),
+    "msm_sim_run_streams": (C.c_int, [_vp, C.c_int32, _ip, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.c_uint64]),
     "msm_sim_not_finished": (C.c_int, [_vp]),
     "msm_sim_state": (C.c_int, [_vp, C.c_int32, C.POINTER(MsmStreamState)]),
     "msm_sim_get_psi": (C.c_int, [_vp, C.c_int32, _dp, _dp]),

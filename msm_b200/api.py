@@ -146,6 +146,23 @@ class Context:
         ip = (_dp * n)(*[_f64(a.reshape(-1)) for a in im])
         self._chk(lib.msm_get_psi_many(self.handle, n, ids.ctypes.data_as(_ip), rp, ip))
 
+    # asynchronous transfers: the arrays must stay alive (and unmodified) until transfers_wait() returns
+    def upload_begin(self, stream: int, psi_flat: np.ndarray) -> None:
+        assert psi_flat.size == 2 * self.cells
+        self._chk(lib.msm_upload_begin(self.handle, stream, _f64(psi_flat)))
+
+    def download_begin(self, stream: int, re: Optional[np.ndarray], im: Optional[np.ndarray]) -> None:
+        self._chk(lib.msm_download_begin(self.handle, stream, _f64(re.reshape(-1)) if re is not None else None,
+                                         _f64(im.reshape(-1)) if im is not None else None))
+
+    def transfers_wait(self) -> None:
+        self._chk(lib.msm_transfers_wait(self.handle))
+
+    def chunk_streams(self) -> int:
+        v = C.c_int32()
+        self._chk(lib.msm_chunk_streams(self.handle, C.byref(v)))
+        return v.value
+
     def get_psik(self, stream: int) -> np.ndarray:
         out = np.empty(self.shape, dtype=np.complex128)
         self._chk(lib.msm_get_psik_interleaved(self.handle, stream, _f64(out.reshape(-1).view(np.float64))))
@@ -343,6 +360,42 @@ class SimulationObject:
     def update(self, raise_on_alias: bool = True) -> None:
         """One `update()` for every unfinished stream."""
         code = lib.msm_sim_update(self.handle)
+        if code == _lib.MSM_E_ALIASING:
+            if raise_on_alias:
+                raise FourierAliasing(code, lib.msm_sim_last_error(self.handle).decode())
+            return
+        check(code, self.handle, sim=True)
+
+    def update_streams(self, subset: Sequence[int], raise_on_alias: bool = True) -> None:
+        """One `update()` for the unfinished streams with subset[s] != 0."""
+        arr = np.ascontiguousarray(subset, dtype=np.int32)
+        assert arr.size == self.n_streams
+        code = lib.msm_sim_update_streams(self.handle, arr.ctypes.data_as(_ip))
+        if code == _lib.MSM_E_ALIASING:
+            if raise_on_alias:
+                raise FourierAliasing(code, lib.msm_sim_last_error(self.handle).decode())
+            return
+        check(code, self.handle, sim=True)
+
+    def run_streams(self, streams: Sequence[int], psi_in: Optional[Sequence[Optional[np.ndarray]]] = None,
+                    re_out: Optional[Sequence[Optional[np.ndarray]]] = None,
+                    im_out: Optional[Sequence[Optional[np.ndarray]]] = None, max_updates: int = 0,
+                    raise_on_alias: bool = True) -> None:
+        """The reference's outer loop (simulator/src/main.rs:43-85) for the listed streams: upload psi_in[i] (flat
+        float64 views of complex128 grids), `while not_finished(): update()` (at most max_updates per stream when > 0),
+        final psi into re_out[i] / im_out[i].  Transfers of neighbouring stream groups overlap the step kernels."""
+        n = len(streams)
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+
+        def ptrs(arrs):
+            if arrs is None:
+                return None
+            assert len(arrs) == n
+            return (_dp * n)(*[_f64(a.reshape(-1)) if a is not None else None for a in arrs])
+        for a in (psi_in or []):
+            assert a is None or a.size == 2 * self.grid.cells
+        code = lib.msm_sim_run_streams(self.handle, n, ids.ctypes.data_as(_ip), ptrs(psi_in), ptrs(re_out), ptrs(im_out),
+                                       int(max_updates))
         if code == _lib.MSM_E_ALIASING:
             if raise_on_alias:
                 raise FourierAliasing(code, lib.msm_sim_last_error(self.handle).decode())

@@ -365,6 +365,19 @@ struct msm_ctx {
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;
     cudaStream_t copy_st = nullptr;                       // msm_get_psi_many: D2H overlapped with compute
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    // asynchronous transfers (msm_upload_begin / msm_download_begin): PCIe traffic of other streams overlaps the
+    // step kernels.  Uploads run on up_st (staging + relayout when the device layout is blocked) and signal one
+    // event per stream; downloads are transformed / plane-split on the compute stream into two dedicated staging
+    // buffers and leave on copy_st.
+    cudaStream_t up_st = nullptr;
+    std::vector<cudaEvent_t> up_ev;
+    std::vector<char> up_pending;
+    cudaEvent_t ev_x_free = nullptr;
+    double2* up_stage = nullptr;
+    double* dl_stage[2] = {nullptr, nullptr};
+    cudaEvent_t dl_ready[2] = {nullptr, nullptr}, dl_copied[2] = {nullptr, nullptr};
+    char dl_used[2] = {0, 0};
+    int dl_next = 0;
     // profiling
     bool prof = false;
     std::vector<ProfEvent> prof_pending;
@@ -610,9 +623,20 @@ int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2*
 
 int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
 
+// the compute stream must not touch X[s] before an asynchronous upload of stream s has landed
+int wait_upload(msm_ctx* ctx, int s) {
+    if (!ctx->up_pending.empty() && ctx->up_pending[s]) {
+        if (cudaStreamWaitEvent(ctx->st, ctx->up_ev[s], 0) != cudaSuccess)
+            return fail(ctx, MSM_E_CUDA, "cudaStreamWaitEvent(upload) failed");
+        ctx->up_pending[s] = 0;
+    }
+    return MSM_OK;
+}
+
 int ensure_kspace(msm_ctx* ctx, const std::vector<int>& ids) {
     std::vector<int> todo;
     for (int s : ids) {
+        if (int rc = wait_upload(ctx, s)) return rc;
         if (!ctx->has_psi[s]) return fail(ctx, MSM_E_STATE, "stream has no wavefunction (call msm_set_psi first)");
         if (!ctx->in_k[s]) todo.push_back(s);
     }
@@ -904,6 +928,7 @@ void msm_destroy(msm_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->copy_st) cudaStreamSynchronize(ctx->copy_st);
     prof_drain(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     cudaFree(ctx->X);
@@ -928,6 +953,19 @@ void msm_destroy(msm_ctx* ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     }
     if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
+    if (ctx->up_st) {
+        cudaStreamSynchronize(ctx->up_st);
+        cudaStreamDestroy(ctx->up_st);
+    }
+    for (cudaEvent_t e : ctx->up_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->ev_x_free) cudaEventDestroy(ctx->ev_x_free);
+    cudaFree(ctx->up_stage);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ctx->dl_stage[i]);
+        if (ctx->dl_ready[i]) cudaEventDestroy(ctx->dl_ready[i]);
+        if (ctx->dl_copied[i]) cudaEventDestroy(ctx->dl_copied[i]);
+    }
     if (ctx->tm_a) cudaEventDestroy(ctx->tm_a);
     if (ctx->tm_b) cudaEventDestroy(ctx->tm_b);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -950,6 +988,7 @@ int msm_synchronize(msm_ctx* ctx) {
 int msm_set_psi(msm_ctx* ctx, int32_t s, const double* psi) {
     if (!ctx || !psi || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_set_psi: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
     if (ctx->lb == 0) {
         CU(cudaMemcpyAsync(ctx->X + (size_t)s * ctx->C, psi, sizeof(double2) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
     } else {   // host layout is linear, device layout blocked: stage through scratch slot 0
@@ -968,6 +1007,7 @@ int msm_set_psi(msm_ctx* ctx, int32_t s, const double* psi) {
 int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* im) {
     if (!ctx || !re || !im || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_set_psi_planes: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
     double* stage = reinterpret_cast<double*>(ctx->Tscr);   // 2*C doubles = one scratch slot
     CU(cudaMemcpyAsync(stage, re, sizeof(double) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(stage + ctx->C, im, sizeof(double) * (size_t)ctx->C, cudaMemcpyHostToDevice, ctx->st));
@@ -984,6 +1024,7 @@ int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* 
 // psi of stream s into scratch slot 0 (or X itself when no transform has happened yet); returns the device pointer
 static int psi_on_device(msm_ctx* ctx, int s, const double2** out, int slot = 0) {
     if (!ctx->has_psi[s]) return fail(ctx, MSM_E_STATE, "stream has no wavefunction");
+    if (int rc = wait_upload(ctx, s)) return rc;
     if (!ctx->in_k[s]) {
         *out = ctx->X + (size_t)s * ctx->C;
         return MSM_OK;
@@ -1073,6 +1114,104 @@ int msm_get_psi_many(msm_ctx* ctx, int32_t n, const int32_t* streams, double* co
     }
     CU(cudaStreamSynchronize(ctx->copy_st));
     CU(cudaStreamSynchronize(ctx->st));
+    return MSM_OK;
+}
+
+// ---- asynchronous transfers ------------------------------------------------------------------------------------
+int msm_chunk_streams(const msm_ctx* ctx, int32_t* chunk) {
+    if (!ctx || !chunk) return MSM_E_ARG;
+    *chunk = ctx->chunk;
+    return MSM_OK;
+}
+
+int msm_upload_begin(msm_ctx* ctx, int32_t s, const double* psi) {
+    if (!ctx || !psi || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_upload_begin: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const size_t cb = sizeof(double2) * (size_t)ctx->C;
+    if (!ctx->up_st) {
+        CU(cudaStreamCreateWithFlags(&ctx->up_st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_x_free, cudaEventDisableTiming));
+        ctx->up_ev.assign(ctx->S, nullptr);
+        ctx->up_pending.assign(ctx->S, 0);
+    }
+    if (ctx->lb != 0 && !ctx->up_stage) {
+        if (cudaMalloc(&ctx->up_stage, cb) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, MSM_E_NOMEM, "msm_upload_begin: no memory for the upload staging buffer");
+        }
+        ctx->bytes += cb;
+    }
+    if (!ctx->up_ev[s]) CU(cudaEventCreateWithFlags(&ctx->up_ev[s], cudaEventDisableTiming));
+    // X[s] may still be read by work already enqueued on the compute stream: order the upload behind it
+    CU(cudaEventRecord(ctx->ev_x_free, ctx->st));
+    CU(cudaStreamWaitEvent(ctx->up_st, ctx->ev_x_free, 0));
+    double2* dst = ctx->X + (size_t)s * ctx->C;
+    if (ctx->lb == 0) {
+        CU(cudaMemcpyAsync(dst, psi, cb, cudaMemcpyHostToDevice, ctx->up_st));
+    } else {
+        CU(cudaMemcpyAsync(ctx->up_stage, psi, cb, cudaMemcpyHostToDevice, ctx->up_st));
+        k_relayout<<<grid_for(ctx->C), 256, 0, ctx->up_st>>>(ctx->up_stage, dst, ctx->C, ctx->n, ctx->lb, 1);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ctx->up_ev[s], ctx->up_st));
+    ctx->up_pending[s] = 1;
+    ctx->in_k[s] = 0;
+    ctx->has_psi[s] = 1;
+    ctx->pmax_valid[s] = 0;
+    return MSM_OK;
+}
+
+int msm_download_begin(msm_ctx* ctx, int32_t s, double* re, double* im) {
+    if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_download_begin: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const size_t pb = sizeof(double) * (size_t)ctx->C;
+    if (!ctx->copy_st) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    if (!ctx->dl_stage[0]) {
+        for (int i = 0; i < 2; ++i) {
+            if (cudaMalloc(&ctx->dl_stage[i], 2 * pb) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, MSM_E_NOMEM, "msm_download_begin: no memory for the download staging buffers");
+            }
+            ctx->bytes += 2 * pb;
+            CU(cudaEventCreateWithFlags(&ctx->dl_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->dl_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const int b = ctx->dl_next;
+    ctx->dl_next ^= 1;
+    if (ctx->dl_used[b]) CU(cudaStreamWaitEvent(ctx->st, ctx->dl_copied[b], 0));   // staging b has left the device
+    const double2* d = nullptr;
+    int rc = psi_on_device(ctx, s, &d, ctx->chunk >= 2 ? b : 0);
+    if (rc) return rc;
+    double* planes = ctx->dl_stage[b];
+    k_deinterleave<<<grid_for(ctx->C), 256, 0, ctx->st>>>(d, planes, planes + ctx->C, ctx->C, ctx->n, ctx->lb);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->dl_ready[b], ctx->st));
+    CU(cudaStreamWaitEvent(ctx->copy_st, ctx->dl_ready[b], 0));
+    if (re) CU(cudaMemcpyAsync(re, planes, pb, cudaMemcpyDeviceToHost, ctx->copy_st));
+    if (im) CU(cudaMemcpyAsync(im, planes + ctx->C, pb, cudaMemcpyDeviceToHost, ctx->copy_st));
+    CU(cudaEventRecord(ctx->dl_copied[b], ctx->copy_st));
+    ctx->dl_used[b] = 1;
+    return MSM_OK;
+}
+
+int msm_transfers_wait(msm_ctx* ctx) {
+    if (!ctx) return MSM_E_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->up_st) CU(cudaStreamSynchronize(ctx->up_st));
+    if (ctx->copy_st) {
+        // downloads are produced on the compute stream: everything enqueued there has to reach the copy stream first
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaStreamSynchronize(ctx->copy_st));
+    }
     return MSM_OK;
 }
 
@@ -1417,6 +1556,7 @@ static int normalize_on_device(msm_ctx* ctx, double2* psi) {
 int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double* std) {
     if (!ctx || !mean || !std || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_cold_gauss: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
     const int n = ctx->n, d = ctx->dims;
     const double dx = ctx->cfg.dx;
     // 1-D factors, each normalised with dx^dims as the reference does (ics.rs:91,110,132)
@@ -1450,6 +1590,7 @@ int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double*
 int msm_ic_cold_gauss_kspace(msm_ctx* ctx, int32_t s, const double* mean, const double* std, uint64_t phase_seed) {
     if (!ctx || !mean || !std || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_cold_gauss_kspace: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
     const int n = ctx->n, d = ctx->dims;
     const double dk = ctx->cfg.dx;   // dk = dx in the reference (simulation_object.rs:263)
     if (3 * n > 4096) return fail(ctx, MSM_E_ARG, "size too large for the IC staging buffer");
@@ -1492,6 +1633,7 @@ int msm_ic_cold_gauss_kspace(msm_ctx* ctx, int32_t s, const double* mean, const 
 int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t s, double axis_length, double radius, double delta, double slope) {
     if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_spherical_tophat: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
     double2* psi = ctx->X + (size_t)s * ctx->C;
     const double dx = axis_length / (double)ctx->n;   // ics.rs:203 (axis length, not the comoving box)
     k_ic_tophat<<<grid_for(ctx->C), 256, 0, ctx->st>>>(psi, ctx->n, ctx->dims, dx, axis_length / 2.0, radius, delta, slope, ctx->lb);
@@ -1509,6 +1651,8 @@ int msm_ic_copy(msm_ctx* ctx, int32_t dst, int32_t src) {
     if (!ctx || dst < 0 || dst >= ctx->S || src < 0 || src >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_copy: bad argument");
     if (!ctx->has_psi[src]) return fail(ctx, MSM_E_STATE, "msm_ic_copy: source stream is empty");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, src)) return rc;
+    if (int rc = wait_upload(ctx, dst)) return rc;
     if (dst != src)
         CU(cudaMemcpyAsync(ctx->X + (size_t)dst * ctx->C, ctx->X + (size_t)src * ctx->C, sizeof(double2) * (size_t)ctx->C,
                            cudaMemcpyDeviceToDevice, ctx->st));
@@ -1529,6 +1673,7 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     const double sqrt_dv = sqrt(pow(ctx->cfg.dx, (double)ctx->dims));
     const double div = sqrt(n_tot) * (scheme == MSM_SCHEME_WIGNER ? 2.0 : sqrt(2.0));   // ics.rs:581 / :625
     ctx->pmax_valid[s] = 0;
+    if (int rc = wait_upload(ctx, s)) return rc;
     k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div, ctx->n, ctx->lb);
     ctx->launches++;
     CU(cudaGetLastError());

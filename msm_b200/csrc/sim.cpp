@@ -12,6 +12,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <functional>
 #include <string>
 #include <thread>
@@ -341,14 +342,15 @@ int msm_sim_not_finished(const msm_sim* sim) {
     return 0;
 }
 
-int msm_sim_update(msm_sim* sim) {
-    if (!sim) return MSM_E_ARG;
+// one `update()` (:475 / :669) for every unfinished stream of `subset` (NULL = all streams)
+static int update_streams(msm_sim* sim, const int32_t* subset) {
     const msm_sim_params& p = sim->p;
     const int S = p.n_streams;
     const bool summed = p.coupling == MSM_COUPLING_SUMMED;
     std::vector<int32_t> active(S, 0);
     int nact = 0;
     for (int s = 0; s < S; ++s) {
+        if (subset && !subset[s]) continue;
         sim->st[s].dumped = 0;
         if (not_finished(sim, sim->st[s])) {
             active[s] = 1;
@@ -425,6 +427,114 @@ int msm_sim_update(msm_sim* sim) {
         }
         st.n_steps += 1;                                                         // :635 / :797
     }
+    return result;
+}
+
+int msm_sim_update(msm_sim* sim) {
+    if (!sim) return MSM_E_ARG;
+    return update_streams(sim, nullptr);
+}
+
+int msm_sim_update_streams(msm_sim* sim, const int32_t* subset) {
+    if (!sim) return MSM_E_ARG;
+    if (subset && sim->p.coupling == MSM_COUPLING_SUMMED)
+        return sfail(sim, MSM_E_ARG, "msm_sim_update_streams: summed coupling advances all streams together");
+    return update_streams(sim, subset);
+}
+
+// The reference's outer loop (simulator/src/main.rs:43-85): for every stream of the TOML, build the IC, construct the
+// SimulationObject (new_from_params, simulation_object.rs:404-449), `while not_finished() { update() }` (main.rs:65-69)
+// and write the final state.  The reference runs the streams strictly one after another; here they advance in groups
+// of up to chunk_streams, and while group c computes, the ICs of group c+1 cross PCIe on the upload stream and the final
+// wavefunctions of group c-1 leave on the copy stream (one download enqueued after every update, so that the two
+// staging buffers never stall the step kernels).
+int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const double* const* psi_in, double* const* re_out,
+                        double* const* im_out, uint64_t max_updates) {
+    if (!sim || n < 0 || (n > 0 && !streams)) return sfail(sim, MSM_E_ARG, "msm_sim_run_streams: bad argument");
+    const msm_sim_params& p = sim->p;
+    const int S = p.n_streams;
+    if (p.coupling == MSM_COUPLING_SUMMED)
+        return sfail(sim, MSM_E_ARG, "msm_sim_run_streams: streams are coupled (summed density); use msm_sim_update");
+    std::vector<char> seen(S, 0);
+    for (int i = 0; i < n; ++i) {
+        if (streams[i] < 0 || streams[i] >= S || seen[streams[i]])
+            return sfail(sim, MSM_E_ARG, "msm_sim_run_streams: stream out of range or listed twice");
+        seen[streams[i]] = 1;
+    }
+    if (n == 0) return MSM_OK;
+    int32_t chunk = 1;
+    msm_chunk_streams(sim->ctx, &chunk);
+    // group size: the launch chunk when there are enough streams to pipeline (>= 4 groups), else smaller (even) groups
+    int g = chunk;
+    if (n < 4 * g) g = std::max(2, (n / 4) & ~1);
+    g = std::max(1, std::min(g, (int)chunk));
+    const int ngroups = (n + g - 1) / g;
+    auto has_out = [&](int i) { return (re_out && re_out[i]) || (im_out && im_out[i]); };
+    auto gfail = [&](int rc) {
+        sim->err = msm_last_error(sim->ctx);
+        msm_transfers_wait(sim->ctx);
+        return rc;
+    };
+    auto upload_group = [&](int c) -> int {
+        for (int i = c * g; i < std::min(n, (c + 1) * g); ++i) {
+            if (!psi_in || !psi_in[i]) continue;
+            Stream fresh;                                                        // a new SimulationObject (:404-449)
+            fresh.time = p.time;
+            fresh.tau = sim->d.tau0;
+            if (p.expanding) fresh.solver = ScaleFactorSolver(sim->cosmo);
+            sim->st[streams[i]] = fresh;
+            if (int rc = msm_upload_begin(sim->ctx, streams[i], psi_in[i])) return rc;
+        }
+        return MSM_OK;
+    };
+    std::vector<int> pending;   // indices whose final psi still has to leave the device
+    size_t pending_pos = 0;
+    auto download_some = [&](size_t count) -> int {
+        for (; count > 0 && pending_pos < pending.size(); --count, ++pending_pos) {
+            const int i = pending[pending_pos];
+            if (int rc = msm_download_begin(sim->ctx, streams[i], re_out ? re_out[i] : nullptr, im_out ? im_out[i] : nullptr))
+                return rc;
+        }
+        return MSM_OK;
+    };
+    int result = MSM_OK;
+    std::string alias_text;
+    int rc = upload_group(0);
+    if (rc) return gfail(rc);
+    for (int c = 0; c < ngroups; ++c) {
+        if (c + 1 < ngroups && (rc = upload_group(c + 1))) return gfail(rc);
+        std::vector<int32_t> mask(S, 0);
+        const int lo = c * g, hi = std::min(n, (c + 1) * g);
+        // downloads of the previous group per update of this one (all of them when this group has nothing to do)
+        const size_t left = pending.size() - pending_pos;
+        const size_t per_update = max_updates ? (left + max_updates - 1) / max_updates : 1;
+        for (uint64_t u = 0; max_updates == 0 || u < max_updates; ++u) {
+            int nact = 0;
+            for (int i = lo; i < hi; ++i) {
+                const Stream& st = sim->st[streams[i]];
+                mask[streams[i]] = (not_finished(sim, st) && !st.aliased) ? 1 : 0;   // the reference aborts on aliasing (:607-617)
+                nact += mask[streams[i]];
+            }
+            if (!nact) break;
+            rc = update_streams(sim, mask.data());
+            if (rc == MSM_E_ALIASING) {
+                result = rc;
+                alias_text = sim->err;
+            } else if (rc) {
+                msm_transfers_wait(sim->ctx);
+                return rc;
+            }
+            if ((rc = download_some(per_update))) return gfail(rc);
+        }
+        if ((rc = download_some(pending.size()))) return gfail(rc);
+        pending.clear();
+        pending_pos = 0;
+        for (int i = lo; i < hi; ++i)
+            if (has_out(i)) pending.push_back(i);
+    }
+    if ((rc = download_some(pending.size()))) return gfail(rc);
+    if ((rc = msm_transfers_wait(sim->ctx))) return gfail(rc);
+    if (result == MSM_E_ALIASING) sim->err = alias_text;
     return result;
 }
 

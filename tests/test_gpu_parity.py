@@ -8,6 +8,7 @@ Tolerances (fp64, relative L2 unless noted; measured values are ~1e-15, see DESI
   alias mass                      <= 1e-10 relative or 1e-30 absolute (it is round-off noise when nothing aliases)
   trajectories (up to 200 steps)  <= 1e-10   (the north-star bound)
 """
+import copy
 import os
 
 import numpy as np
@@ -296,6 +297,104 @@ def test_streams_finish_at_different_steps():
     assert sim.state(0).n_steps == refs[0].parameters.n_steps != refs[1].parameters.n_steps == sim.state(1).n_steps
     for i, r in enumerate(refs):
         assert rel_l2(sim.get_psi(i), r.psi) < 1e-10
+    sim.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pipelined outer loop (simulator/src/main.rs:43-85): uploads / downloads of neighbouring groups overlap the steps
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nstreams,chunk,max_updates,lb", [(11, 2, 3, 0), (16, 4, 0, 0), (5, 8, 1, 0), (9, 4, 2, 2),
+                                                           (1, 0, 2, 0)])
+def test_run_streams_matches_oracle_and_the_sequential_path(monkeypatch, nstreams, chunk, max_updates, lb):
+    if lb:
+        monkeypatch.setenv("MSM_B200_LB", str(lb))
+    its = oracle_streams("spherical-tophat")
+    ps = its[:nstreams]
+    for p in ps:
+        p.final_sim_time, p.num_data_dumps = 1.0, 5          # 5 updates to the end (every step hits a dump)
+    psi0s = [initial_wavefunction(p) for p in ps]
+    flat = [np.ascontiguousarray(a).reshape(-1).view(np.float64).copy() for a in psi0s]
+    re = [np.zeros(psi0s[0].shape) for _ in ps]
+    im = [np.zeros(psi0s[0].shape) for _ in ps]
+    order = list(range(nstreams))[::-1] if nstreams % 2 else list(range(nstreams))      # any order of slots
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=nstreams, chunk_streams=chunk)
+    sim.run_streams(order, [flat[s] for s in order], [re[s] for s in order], [im[s] for s in order], max_updates)
+    for s, p in enumerate(ps):
+        r = o.SimulationObject(copy.deepcopy(p), psi0s[s])     # the oracle advances its parameters in place
+        k = 0
+        while r.not_finished() and (max_updates == 0 or k < max_updates):
+            r.update()
+            k += 1
+        st = sim.state(s)
+        assert st.n_steps == k and (max_updates == 0 or k == max_updates)
+        assert st.finished == (0 if r.not_finished() else 1)
+        assert abs(st.time - r.parameters.time) <= 1e-13 * abs(r.parameters.time)
+        assert rel_l2(re[s] + 1j * im[s], r.psi) < 1e-10
+        assert rel_l2(sim.get_psi(s), re[s] + 1j * im[s]) < 1e-14       # the download is the resident state
+    # continue the same streams without new ICs: state carries over
+    if max_updates:
+        sim.run_streams(order, None, [re[s] for s in order], None, 0)
+        for s, p in enumerate(ps):
+            r = o.SimulationObject(copy.deepcopy(p), psi0s[s])
+            while r.not_finished():
+                r.update()
+            assert sim.state(s).finished == 1 and sim.state(s).n_steps == r.parameters.n_steps
+            assert rel_l2(re[s], r.psi.real) < 1e-10
+    # a second run from fresh ICs restarts time and dumps (a new SimulationObject per stream, :404-449)
+    sim.run_streams(order[:1], [flat[order[0]]], None, None, 1)
+    st = sim.state(order[0])
+    assert st.n_steps == 1 and st.current_dumps == 1
+    sim.close()
+
+
+def test_async_transfers_order_against_compute():
+    """msm_upload_begin / msm_download_begin: uploads land before the compute stream touches the stream, downloads
+    see everything enqueued before them."""
+    ps = oracle_streams("spherical-tophat", 32, limit=4)
+    ctx = make_ctx(ps[0], 4, chunk_streams=2)
+    assert ctx.chunk_streams() == 2
+    psi0s = [initial_wavefunction(p) for p in ps]
+    flat = [np.ascontiguousarray(a).reshape(-1).view(np.float64).copy() for a in psi0s]
+    for s in range(4):
+        ctx.upload_begin(s, flat[s])
+    re = [np.zeros(psi0s[0].shape) for _ in ps]
+    im = [np.zeros(psi0s[0].shape) for _ in ps]
+    hb = ps[0].hbar_
+    alias = ctx.step([0.05 / 4 * hb] * 4, [0.05 / hb] * 4)
+    assert np.all(alias >= 0)
+    for s in range(4):                                   # more downloads than staging buffers
+        ctx.download_begin(s, re[s], im[s])
+    ctx.upload_begin(0, flat[1])                         # overwriting stream 0 must wait for its download
+    ctx.transfers_wait()
+    want = []
+    for s in range(4):
+        ctx2 = make_ctx(ps[0], 2, chunk_streams=2)       # same pairing as above: (0,1) and (2,3)
+        base = (s // 2) * 2
+        ctx2.set_psi(0, psi0s[base])
+        ctx2.set_psi(1, psi0s[base + 1])
+        ctx2.step([0.05 / 4 * hb] * 2, [0.05 / hb] * 2)
+        want.append(ctx2.get_psi(s - base))
+        ctx2.close()
+    for s in range(4):
+        assert np.array_equal(re[s] + 1j * im[s], want[s])
+    assert np.array_equal(ctx.get_psi(0), psi0s[1])
+    ctx.close()
+
+
+def test_run_streams_error_behaviour():
+    ps = oracle_streams("spherical-tophat", limit=2)
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=2)
+    with pytest.raises(m.MsmError) as e:
+        sim.run_streams([0, 0])
+    assert e.value.code == _lib.MSM_E_ARG
+    with pytest.raises(m.MsmError) as e:
+        sim.run_streams([0, 1])                          # no wavefunction uploaded yet
+    assert e.value.code == _lib.MSM_E_STATE
+    sim.close()
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=2, coupling=m.COUPLING_SUMMED)
+    with pytest.raises(m.MsmError) as e:
+        sim.run_streams([0, 1])
+    assert e.value.code == _lib.MSM_E_ARG
     sim.close()
 
 
