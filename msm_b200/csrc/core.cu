@@ -589,7 +589,8 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         p.lvalid = g.lvalid;
         p.ntiles = g.ntiles;
         char nm[96];
-        p.tiles_per_cta = ctx->tiles_per_cta;
+        // consecutive tiles of one CTA must differ by inner_stride only: tiles_per_cta divides tiles_inner
+        p.tiles_per_cta = (int)std::__gcd((long long)ctx->tiles_per_cta, (long long)g.tiles_inner);
         p.l2_prefetch = ctx->l2_prefetch;
         snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s,%s>", ctx->n, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop),
                  axis == 0 ? "x" : axis == 1 ? "y" : "z");
@@ -823,6 +824,9 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
     ctx->lb = (cfg->dims == 3 && n >= 512) ? 4 : 0;
     if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;
+    // the pass kernels address a thread's elements e = t + NT * j (NT = n / 8 threads per line) as a0 + j * step,
+    // which needs NT to be a multiple of the block
+    while (ctx->lb > 0 && (n < 16 || (n / 8) % (1 << ctx->lb))) ctx->lb--;
     ctx->num_sms = prop.multiProcessorCount;
     int chunk = cfg->chunk_streams > 0 ? cfg->chunk_streams : 8;
     chunk = std::min(chunk, MAX_CHUNK);

@@ -1,6 +1,8 @@
 // fft_inst.cu -- instantiates the pass kernels for ONE transform length (compile with -DMSM_FFT_N=<N>).
 #include "fft_pass.cuh"
 
+#include <stdlib.h>
+
 #ifndef MSM_FFT_N
 #error "compile with -DMSM_FFT_N=<power of two>"
 #endif
@@ -24,6 +26,11 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
+        // L1 / shared memory split: the driver default.  Measured: forcing the maximum shared-memory carve-out costs 8 %
+        // (the twiddle and drift tables live in L1); profiles/README.md
+        const char* co = getenv("MSM_B200_CARVEOUT");   // A/B timing: -1 = driver default, 0..100 = percent shared
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             co ? atoi(co) : (int)cudaSharedmemCarveoutDefault);
         configured = true;
     }
     dim3 grid((ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta, groups, 1);

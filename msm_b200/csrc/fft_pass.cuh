@@ -109,7 +109,10 @@ MSM_PLAN(64,   8, 8,  1, 2, 8, 8, 1, 1)
 MSM_PLAN(128,  8, 8,  1, 3, 2, 8, 8, 1)
 MSM_PLAN(256,  8, 8,  2, 3, 4, 8, 8, 1)
 // 512: E = 8 / 2 CTAs per SM measured best (E = 16: -3 %, E = 32 with 3 CTAs: -27 %; profiles/README.md)
-MSM_PLAN(512,  8, 8,  2, 3, 8, 8, 8, 1)
+#ifndef MSM_MINB512
+#define MSM_MINB512 2
+#endif
+MSM_PLAN(512,  8, 8,  MSM_MINB512, 3, 8, 8, 8, 1)
 MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #undef MSM_PLAN
 
@@ -122,7 +125,14 @@ MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #endif
 template <int N, bool XL> constexpr int tile_T() { return (XL && N >= 256 && Plan<N>::T == 8) ? MSM_TX : Plan<N>::T; }
 template <int N, bool XL> constexpr int tile_threads() { return Plan<N>::NT * tile_T<N, XL>(); }
-template <int N, bool XL> constexpr int tile_minb() { return Plan<N>::MINB * (Plan<N>::T / tile_T<N, XL>()); }
+// Resident CTAs the small-tile contiguous-axis kernels are compiled for.  Measured (profiles/README.md): 4 CTAs per SM
+// with 128 registers beat 8 CTAs with 64 (spills, no room to overlap loads with butterflies): +8 % on the whole step.
+#ifndef MSM_XL_MINB
+#define MSM_XL_MINB 4
+#endif
+template <int N, bool XL> constexpr int tile_minb() {
+    return (XL && tile_T<N, XL>() != Plan<N>::T) ? MSM_XL_MINB : Plan<N>::MINB * (Plan<N>::T / tile_T<N, XL>());
+}
 
 template <int N> constexpr int plan_L(int q) {   // product of radices of stages < q
     int l = 1;
@@ -295,12 +305,27 @@ template <int N, bool XL> __device__ __forceinline__ int sm_index(int pos, int l
 // of the tile.  Otherwise the lines are interleaved across all warps: CTA-wide barrier.
 template <int N, bool XL> __device__ __forceinline__ void exchange_barrier(int l) {
     if constexpr (XL && (Plan<N>::NT % 32 == 0)) {
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + l), "n"(Plan<N>::NT) : "memory");
+        // The barrier id must be an IMMEDIATE: with a register operand ptxas cannot tell which barriers the kernel
+        // uses and reserves all 16 for every CTA ("used 16 barriers"), and an SM has 64 barrier slots -> 4 CTAs per SM
+        // instead of 8 (ncu: 16 resident warps; profiles/README.md).  The branch is warp-uniform (a warp = one line).
+        constexpr int T = tile_T<N, true>();
+        static_assert(T <= 8, "one named barrier per line");
+#define MSM_LINE_BAR(ID)                                                                      \
+    if (T > ID && l == ID) asm volatile("bar.sync %0, %1;" ::"n"(1 + ID), "n"(Plan<N>::NT) : "memory");
+        MSM_LINE_BAR(0) MSM_LINE_BAR(1) MSM_LINE_BAR(2) MSM_LINE_BAR(3)
+        MSM_LINE_BAR(4) MSM_LINE_BAR(5) MSM_LINE_BAR(6) MSM_LINE_BAR(7)
+#undef MSM_LINE_BAR
     } else {
         __syncthreads();
     }
 }
 
+// Twiddle tables are copied to shared memory once per CTA (N * 16 bytes): an L1 hit costs a long-scoreboard wait after
+// every butterfly stage, an LDS does not (measured +4.5 % on the whole step; MSM_TW_SMEM=0 reads them through L1)
+#ifndef MSM_TW_SMEM
+#define MSM_TW_SMEM 1
+#endif
+constexpr bool kTwSmem = MSM_TW_SMEM != 0;
 template <int N, bool INV, bool XL, int Q>
 __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm, int t, int l,
                                            const double2* __restrict__ tw) {
@@ -322,7 +347,8 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
             for (int k = 0; k < R; ++k) {
                 double2 x = v[c * R + k];
                 if (k > 0) {
-                    double2 w = __ldg(&tw[plan_tw_offset<N>(Q) + (k - 1) * M + nu]);
+                    double2 w = kTwSmem ? tw[plan_tw_offset<N>(Q) + (k - 1) * M + nu]
+                                        : __ldg(&tw[plan_tw_offset<N>(Q) + (k - 1) * M + nu]);
                     if (INV) w.y = -w.y;
                     x = cmul(x, w);
                 }
@@ -382,7 +408,7 @@ template <int N, int LOP, bool XL> constexpr int exchange_elems() {
                            : (LOP == L_KICK_IX ? (Plan<N>::E * tile_threads<N, XL>() + 1) / 2 : 0);
 }
 template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {
-    return sizeof(double2) * exchange_elems<N, LOP, XL>() +
+    return sizeof(double2) * exchange_elems<N, LOP, XL>() + (kTwSmem ? sizeof(double2) * N : 0) +
            (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * tile_threads<N, XL>() : 0);
 }
 
@@ -400,8 +426,15 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     extern __shared__ double2 sm[];
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
-    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>());
+    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>() + (kTwSmem ? N : 0));
     __shared__ double red[2][32], red2[32];
+    const double2* tw_base = p.twiddle;
+    if constexpr (kTwSmem) {
+        double2* tws = sm + exchange_elems<N, LOP, XL>();
+        for (int i = threadIdx.x; i < N; i += tile_threads<N, XL>()) tws[i] = p.twiddle[i];
+        __syncthreads();
+        tw_base = tws;
+    }
     double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
     int item_parity = 0;
 
@@ -411,8 +444,6 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     const bool lv = l < p.lvalid;
     const int g = blockIdx.y;
 
-    // L2 prefetch of one tile: the CTA's 512 threads cover the tile's 128-byte lines (strided axes: one line per
-    // position e; contiguous axis: the tile is T * N * 16 contiguous bytes).
     auto tile_origin = [&](int tile_) -> long long {
         const int o = tile_ / p.tiles_inner;
         return (long long)(o >> p.olb) * p.outer_stride + (long long)(o & ((1 << p.olb) - 1)) * p.outer_lo +
@@ -421,21 +452,33 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     auto along = [&](int e) -> long long {
         return (long long)(e >> p.alb) * p.astride + (long long)(e & ((1 << p.alb) - 1)) * p.astride_lo;
     };
-    auto prefetch_tile = [&](const double2* arr, int tile_) {
-        const long long o = tile_origin(tile_);
-        if (XL) {
-            for (int j = tid; j < (N * T) / 8; j += THREADS)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(arr + o + (long long)j * 8));
-        } else {
-            for (int e = tid; e < N; e += THREADS)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(arr + o + along(e)));
-        }
+    // Every element this thread loads or stores has index e = t + NT * j (j < E) along the pass axis, and NT is a
+    // multiple of the slow-axis block (msm_create clamps the block), so its offset is affine in j: a0 + j * astep,
+    // 32-bit element units inside one grid (C <= 2^30).  One IMAD + one IMAD.WIDE per access instead of the general
+    // (hi, lo) split -- the pass kernels are bound by issue slots and latency, not by HBM (profiles/README.md).
+    const int a0 = XL ? t : (int)along(t);
+    const int astep = XL ? NT : (int)((long long)(NT >> p.alb) * p.astride);
+#ifdef MSM_ADDR_GENERAL   // A/B builds: the general (hi, lo) split, 64-bit, recomputed per access
+    auto eoff = [&](int j) -> long long { return along(t + NT * j); };
+#else
+    auto eoff = [&](int j) -> int { return a0 + j * astep; };
+#endif
+    // lines beyond lvalid (1-D grids only) read line 0 again and store nothing
+    const int la = lv ? l : 0;
+    // L2 prefetch of one tile, one 128-byte line per thread (THREADS == N on the strided axes: one line per position;
+    // contiguous axis: the tile is T * N * 16 = THREADS * 128 contiguous bytes)
+    const int pf_off = XL ? tid * 8 : (int)along(tid < N ? tid : 0);
+    auto prefetch_tile = [&](const double2* arr_at_origin) {
+        if (XL ? tid < (N * T) / 8 : tid < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(arr_at_origin + pf_off));
     };
 
+    // the host makes tiles_per_cta a divisor of tiles_inner: consecutive tiles of one CTA differ by inner_stride
+    long long origin = tile_origin(blockIdx.x * p.tiles_per_cta) - p.inner_stride;
     for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
     const int tile = blockIdx.x * p.tiles_per_cta + ti;
     if (tile >= p.ntiles) break;
-    const long long base = tile_origin(tile) + (long long)l * p.lstride;
+    origin += p.inner_stride;
+    const long long base = origin + (long long)la * p.lstride;
 
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
     double kline = 0.0;
@@ -483,20 +526,22 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
         if (li >= p.ns) break;
         const int s = p.sid[li];
         const bool last_of_group = (q + 1 == p.gsz) || (li + 1 >= p.ns);
-        const double2* __restrict__ src = p.src + (long long)(p.src_by_sid ? s : li) * p.src_sstride;
-        double2* __restrict__ dst = p.dst + (long long)(p.dst_by_sid ? s : li) * p.dst_sstride;
+        // pointers to this thread's line of the item; element j of the thread sits at [a0 + j * astep]
+        const double2* __restrict__ src = p.src + (long long)(p.src_by_sid ? s : li) * p.src_sstride + base;
+        double2* __restrict__ dst = p.dst + (long long)(p.dst_by_sid ? s : li) * p.dst_sstride + base;
         double2* __restrict__ pb = p.pbuf + (p.p_summed ? 0 : (long long)g * p.p_gstride);
+        double2* __restrict__ pbl = pb + base;
 
         // pull the NEXT item (partner stream of this tile, else first stream of the next tile) into L2 now, so its
         // loads find the data on chip: DRAM stays busy while this item computes
         if (p.l2_prefetch && (p.tiles_per_cta > 1 || p.gsz > 1)) {
             const bool same_tile = !last_of_group;
-            const int ntile = same_tile ? tile : tile + 1;
             const int nli = same_tile ? li + 1 : g * p.gsz;
-            if (ntile < p.ntiles && (same_tile || ti + 1 < p.tiles_per_cta)) {
+            if (same_tile || (tile + 1 < p.ntiles && ti + 1 < p.tiles_per_cta)) {
                 const int ns_ = p.sid[nli];
-                prefetch_tile(p.src + (long long)(p.src_by_sid ? ns_ : nli) * p.src_sstride, ntile);
-                if ((LOP == L_KICK || LOP == L_KICK_IX) && !same_tile) prefetch_tile(pb, ntile);
+                const long long norigin = same_tile ? origin : origin + p.inner_stride;
+                prefetch_tile(p.src + (long long)(p.src_by_sid ? ns_ : nli) * p.src_sstride + norigin);
+                if ((LOP == L_KICK || LOP == L_KICK_IX) && !same_tile) prefetch_tile(pb + norigin);
             }
         }
 
@@ -509,11 +554,10 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
                 for (int c = 0; c < NB0; ++c) {
 #pragma unroll
                     for (int n = 0; n < R0; ++n) {
-                        const int e = n * M0 + t + NT * c;
-                        v[c * R0 + n] = lv ? pb[base + along(e)] : make_double2(0.0, 0.0);
+                        v[c * R0 + n] = pbl[eoff(c + n * NB0)];
                     }
                 }
-                run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+                run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
                 outputs_to_inputs<N>(v);
                 __syncthreads();   // phi_a slots span the whole exchange buffer: all lines must be done with it
                 double* phia = reinterpret_cast<double*>(sm);
@@ -529,11 +573,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
         for (int c = 0; c < NB0; ++c) {
 #pragma unroll
             for (int n = 0; n < R0; ++n) {
-                const int e = n * M0 + t + NT * c;
-                const long long off = base + along(e);
-                double2 x = make_double2(0.0, 0.0);
-                if (lv) x = src[off];
-                v[c * R0 + n] = x;
+                v[c * R0 + n] = src[eoff(c + n * NB0)];
             }
         }
         if constexpr (LOP == L_DRIFT) {
@@ -564,13 +604,10 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             for (int c = 0; c < NB0; ++c) {
 #pragma unroll
                 for (int n = 0; n < R0; ++n) {
-                    const int e = n * M0 + t + NT * c;
-                    const long long off = base + along(e);
                     double ph;
                     double* slot = &stash[(c * R0 + n) * THREADS + tid];
                     if (q == 0) {
-                        double2 pp = make_double2(0.0, 0.0);
-                        if (lv) pp = pb[off];
+                        const double2 pp = pbl[eoff(c + n * NB0)];
                         ph = pp.x;
                         if (!last_of_group) *slot = p.p_summed ? pp.x : pp.y;
                     } else {
@@ -583,7 +620,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             }
         }
 
-        const double2* tw1 = data_dependent(p.twiddle, v[0].x, p.zero);
+        const double2* tw1 = data_dependent(tw_base, v[0].x, p.zero);
         run_stages<N, INV, XL, 0>(v, sm, t, l, tw1);
 
         if constexpr (SOP == S_POISSON_INV) {
@@ -599,7 +636,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
                 }
             }
             outputs_to_inputs<N>(v);
-            run_stages<N, !INV, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+            run_stages<N, !INV, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
         }
 
         // ---- store (last-stage output order) ----
@@ -609,7 +646,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
 #pragma unroll
             for (int k = 0; k < RL; ++k) {
                 const int e = t + NT * c + LL * k;
-                const long long off = base + along(e);
+                const auto off = eoff(c + k * NBL);
                 double2 x = v[c * RL + k];
                 if constexpr (SOP == S_SCALE) {
                     x.x *= p.scale;
@@ -647,13 +684,13 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
                     } else {
                         const double sum = (q == 0) ? rho : *slot + rho;
                         if (!last_of_group) *slot = sum;
-                        else pair = make_double2((p.rho_accumulate && lv) ? pb[off].x + sum : sum, 0.0);
+                        else pair = make_double2(p.rho_accumulate ? pbl[off].x + sum : sum, 0.0);
                     }
                     if (SOP != S_RHO_ONLY && SOP != S_RHO_ONLY_FX) {
                         if (lv) dst[off] = x;
                     }
                     if (FX) v[c * RL + k] = pair;               // transformed below, after psi has been stored
-                    else if (last_of_group && lv) pb[off] = pair;
+                    else if (last_of_group && lv) pbl[off] = pair;
                 }
                 if constexpr (!sop_is_rho(SOP) && SOP != S_MAX) {
                     if (lv) dst[off] = x;
@@ -666,26 +703,26 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             // first (x) pass of the Poisson solve on the finished pair rho_a + i rho_b, same lines: forward transform
             if (last_of_group) {
                 outputs_to_inputs<N>(v);
-                run_stages<N, false, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+                run_stages<N, false, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
 #pragma unroll
                 for (int c = 0; c < NBL; ++c) {
 #pragma unroll
                     for (int k = 0; k < RL; ++k) {
-                        if (lv) pb[base + along(t + NT * c + LL * k)] = v[c * RL + k];
+                        if (lv) pbl[eoff(c + k * NBL)] = v[c * RL + k];
                     }
                 }
             }
         }
         if constexpr (SOP == S_DRIFT_ALIAS_IZ) {
             // first pass of the next dt-potential: inverse transform of the psi_k just stored, into the scratch slot
-            double2* __restrict__ d2 = p.dst2 + (long long)li * p.dst_sstride;
+            double2* __restrict__ d2 = p.dst2 + (long long)li * p.dst_sstride + base;
             outputs_to_inputs<N>(v);
-            run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(p.twiddle, v[0].x, p.zero));
+            run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
 #pragma unroll
             for (int c = 0; c < NBL; ++c) {
 #pragma unroll
                 for (int k = 0; k < RL; ++k) {
-                    if (lv) d2[base + along(t + NT * c + LL * k)] = v[c * RL + k];
+                    if (lv) d2[eoff(c + k * NBL)] = v[c * RL + k];
                 }
             }
         }

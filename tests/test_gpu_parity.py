@@ -309,7 +309,7 @@ def test_run_streams_matches_oracle_and_the_sequential_path(monkeypatch, nstream
     if lb:
         monkeypatch.setenv("MSM_B200_LB", str(lb))
     its = oracle_streams("spherical-tophat")
-    ps = its[:nstreams]
+    ps = [copy.deepcopy(its[i % len(its)]) for i in range(nstreams)]
     for p in ps:
         p.final_sim_time, p.num_data_dumps = 1.0, 5          # 5 updates to the end (every step hits a dump)
     psi0s = [initial_wavefunction(p) for p in ps]
