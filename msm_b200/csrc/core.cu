@@ -390,6 +390,7 @@ struct msm_ctx {
     bool fuse = true;  // fused passes (MSM_B200_FUSE=0 runs the plain 3+3 pass sequences, for A/B timing)
     int l2_prefetch = 1;   // MSM_B200_PREFETCH=0 switches the L2 prefetch of the next item off (A/B timing)
     int tiles_per_cta = 4;   // consecutive tiles per CTA of the one-tile kernel; next item is prefetched into L2
+    int tiles_per_cta_x = 16;  // the same for the small tiles of the contiguous axis
     int num_sms = 148;
 };
 
@@ -590,7 +591,9 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         p.ntiles = g.ntiles;
         char nm[96];
         // consecutive tiles of one CTA must differ by inner_stride only: tiles_per_cta divides tiles_inner
-        p.tiles_per_cta = (int)std::__gcd((long long)ctx->tiles_per_cta, (long long)g.tiles_inner);
+        // (the contiguous axis has small tiles: more of them per CTA amortise the table preamble)
+        p.tiles_per_cta = (int)std::__gcd((long long)(axis == 0 && ctx->xl ? ctx->tiles_per_cta_x : ctx->tiles_per_cta),
+                                          (long long)g.tiles_inner);
         p.l2_prefetch = ctx->l2_prefetch;
         snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s,%s>", ctx->n, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop),
                  axis == 0 ? "x" : axis == 1 ? "y" : "z");
@@ -819,9 +822,13 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     for (int d = 0; d < cfg->dims; ++d) ctx->C *= n;
     ctx->launcher = get_pass_launcher(n);
     if (const char* e = getenv("MSM_B200_XL")) ctx->xl = atoi(e) != 0;
+    // 1-D grids have one line per tile; the other lines of the tile run as duplicates of it (fft_pass.cuh), which is
+    // only race-free when they share a warp with it: generic thread mapping
+    if (cfg->dims == 1) ctx->xl = false;
     if (const char* e = getenv("MSM_B200_FUSE")) ctx->fuse = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_PREFETCH")) ctx->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
+    if (const char* e = getenv("MSM_B200_TPCX")) ctx->tiles_per_cta_x = std::max(1, atoi(e));
     ctx->lb = (cfg->dims == 3 && n >= 512) ? 4 : 0;
     if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;
     // the pass kernels address a thread's elements e = t + NT * j (NT = n / 8 threads per line) as a0 + j * step,

@@ -26,11 +26,19 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
         }
-        // L1 / shared memory split: the driver default.  Measured: forcing the maximum shared-memory carve-out costs 8 %
-        // (the twiddle and drift tables live in L1); profiles/README.md
-        const char* co = getenv("MSM_B200_CARVEOUT");   // A/B timing: -1 = driver default, 0..100 = percent shared
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             co ? atoi(co) : (int)cudaSharedmemCarveoutDefault);
+        // L1 / shared memory split: ask for exactly what the CTAs this kernel is compiled for need (tables live in shared
+        // memory, L1 only serves spills).  The driver default sometimes leaves room for one CTA less; the maximum
+        // carve-out cost 8 % while the twiddle / drift tables were still read through L1 (profiles/README.md).
+        // MSM_B200_CARVEOUT (A/B timing): -1 = driver default, 0..100 = percent of the maximum.
+        cudaFuncAttributes fa;
+        int pct = (int)cudaSharedmemCarveoutDefault;
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
+            const size_t need = (smem + fa.sharedSizeBytes + 1024) * (size_t)tile_minb<N, XL>();
+            pct = (int)((need * 100 + 227 * 1024 - 1) / (227 * 1024)) + 1;
+            if (pct > 100) pct = 100;
+        }
+        if (const char* co = getenv("MSM_B200_CARVEOUT")) pct = atoi(co);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         configured = true;
     }
     dim3 grid((ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta, groups, 1);

@@ -407,8 +407,17 @@ template <int N, int LOP, bool XL> constexpr int exchange_elems() {
     return Plan<N>::NS > 1 ? (XL ? (N + N / 8) : N) * tile_T<N, XL>()
                            : (LOP == L_KICK_IX ? (Plan<N>::E * tile_threads<N, XL>() + 1) / 2 : 0);
 }
+// Small read-only tables live in shared memory behind the exchange buffer: an L1 hit still costs a long-scoreboard
+// wait at every use (the kernels have no registers to batch such loads), an LDS does not.
+//   twiddles [N] double2 | (k_m)^2 [N] double (k^2 consumers) | drift factors [2][N] double2 (drift operators):
+//   slot q of the drift table belongs to stream q of the CTA's group; groups of more than two streams (summed
+//   coupling) reload slot 0 for every item.
+constexpr bool uses_dtab(int lop, int sop) { return lop == L_DRIFT || sop == S_DRIFT || sop_is_alias(sop); }
+template <int N, int LOP, int SOP> constexpr int table_elems() {   // double2 units
+    return (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0) + (uses_dtab(LOP, SOP) ? 2 * N : 0);
+}
 template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {
-    return sizeof(double2) * exchange_elems<N, LOP, XL>() + (kTwSmem ? sizeof(double2) * N : 0) +
+    return sizeof(double2) * (exchange_elems<N, LOP, XL>() + table_elems<N, LOP, SOP>()) +
            (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * tile_threads<N, XL>() : 0);
 }
 
@@ -426,15 +435,20 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     extern __shared__ double2 sm[];
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
-    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>() + (kTwSmem ? N : 0));
+    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>() + table_elems<N, LOP, SOP>());
     __shared__ double red[2][32], red2[32];
+    double2* tws = sm + exchange_elems<N, LOP, XL>();
+    double* ks = reinterpret_cast<double*>(tws + (kTwSmem ? N : 0));
+    double2* dts = tws + (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0);
     const double2* tw_base = p.twiddle;
     if constexpr (kTwSmem) {
-        double2* tws = sm + exchange_elems<N, LOP, XL>();
         for (int i = threadIdx.x; i < N; i += tile_threads<N, XL>()) tws[i] = p.twiddle[i];
-        __syncthreads();
         tw_base = tws;
     }
+    if constexpr (sop_needs_k2(SOP)) {
+        for (int i = threadIdx.x; i < N; i += tile_threads<N, XL>()) ks[i] = p.ksq[i];
+    }
+    if constexpr (kTwSmem || sop_needs_k2(SOP)) __syncthreads();
     double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
     int item_parity = 0;
 
@@ -444,10 +458,11 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     const bool lv = l < p.lvalid;
     const int g = blockIdx.y;
 
-    auto tile_origin = [&](int tile_) -> long long {
+    // offsets inside one grid fit 32 bits (C <= 2^30 elements); only the stream slot needs 64
+    auto tile_origin = [&](int tile_) -> int {
         const int o = tile_ / p.tiles_inner;
-        return (long long)(o >> p.olb) * p.outer_stride + (long long)(o & ((1 << p.olb) - 1)) * p.outer_lo +
-               (long long)(tile_ % p.tiles_inner) * p.inner_stride;
+        return (int)((long long)(o >> p.olb) * p.outer_stride + (long long)(o & ((1 << p.olb) - 1)) * p.outer_lo +
+                     (long long)(tile_ % p.tiles_inner) * p.inner_stride);
     };
     auto along = [&](int e) -> long long {
         return (long long)(e >> p.alb) * p.astride + (long long)(e & ((1 << p.alb) - 1)) * p.astride_lo;
@@ -460,10 +475,24 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     const int astep = XL ? NT : (int)((long long)(NT >> p.alb) * p.astride);
 #ifdef MSM_ADDR_GENERAL   // A/B builds: the general (hi, lo) split, 64-bit, recomputed per access
     auto eoff = [&](int j) -> long long { return along(t + NT * j); };
+    auto fresh_offsets = [&](double) {};
 #else
-    auto eoff = [&](int j) -> int { return a0 + j * astep; };
+    // The store sections re-derive their offsets from a value that depends on the butterfly results (`dep`; p.zero is
+    // 0, only the compiler does not know): otherwise the store addresses are formed next to the load addresses, live
+    // across the whole transform and get spilled in the register-tight kernels (8 x 64-bit per output array).
+    int a0v = a0;
+    auto eoff = [&](int j) -> int { return a0v + j * astep; };
+#ifdef MSM_NO_FRESH
+    auto fresh_offsets = [&](double) {};
+#else
+    auto fresh_offsets = [&](double dep) { a0v = a0 + (__double2loint(dep) & p.zero); };
 #endif
-    // lines beyond lvalid (1-D grids only) read line 0 again and store nothing
+#endif
+    // Lines beyond lvalid (1-D grids only: one line per tile) are duplicates of line 0: they load the same elements,
+    // compute the same values and store them to the same addresses, and stay out of the reductions (`lv`).  Plain
+    // stores are therefore unconditional -- besides saving the predicate, this avoids a code-generation problem seen with
+    // CUDA 12.9 ptxas for sm_100a: the one `@!P STG.128` it formed from `if (lv) *o = x` at the end of the item body lost
+    // the low word of its data to the next tile's prologue (LDC into the same register).
     const int la = lv ? l : 0;
     // L2 prefetch of one tile, one 128-byte line per thread (THREADS == N on the strided axes: one line per position;
     // contiguous axis: the tile is T * N * 16 = THREADS * 128 contiguous bytes)
@@ -473,15 +502,16 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     };
 
     // the host makes tiles_per_cta a divisor of tiles_inner: consecutive tiles of one CTA differ by inner_stride
-    long long origin = tile_origin(blockIdx.x * p.tiles_per_cta) - p.inner_stride;
+    const int tstride = (int)p.inner_stride, loff = la * (int)p.lstride;
+    int origin = tile_origin(blockIdx.x * p.tiles_per_cta) - tstride;
     for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
     const int tile = blockIdx.x * p.tiles_per_cta + ti;
     if (tile >= p.ntiles) break;
-    origin += p.inner_stride;
-    const long long base = origin + (long long)la * p.lstride;
+    origin += tstride;
+    const int base = origin + loff;
 
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
-    double kline = 0.0;
+    double k_a = 0.0, k_b = 0.0;
     int c0 = 0, c1 = 0, c2 = 0;
     if constexpr (sop_needs_k2(SOP)) {
         const int n = p.n;
@@ -499,16 +529,28 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
         }
         if (!lv) c0 = c1 = c2 = 0;
         // spec_grid sums ((k0^2 + k1^2) + k2^2) * (2 pi)^2 with dim 0 the fastest axis (utils/fft.rs:141-160)
-        if (p.axis == 2) kline = p.ksq[c0] + p.ksq[c1];
+        // one expression for all axes: x + 0 == x exactly, and every term is >= 0
+        if (p.axis == 2) k_a = ks[c0] + ks[c1], k_b = 0.0;
+        else if (p.axis == 1) k_a = ks[c0], k_b = ks[c2];
+        else k_a = ks[c1], k_b = ks[c2];
     }
     auto k2_of = [&](int e) -> double {
-        double s;
-        if (p.axis == 0) s = (p.ksq[e] + p.ksq[c1]) + p.ksq[c2];
-        else if (p.axis == 1) s = (p.ksq[c0] + p.ksq[e]) + p.ksq[c2];
-        else s = kline + p.ksq[e];
-        return s * p.four_pi2;
+        // axis 0: (k[e] + k[c1]) + k[c2];  axis 1: (k[c0] + k[e]) + k[c2];  axis 2: (k[c0] + k[c1]) + k[e]
+        return ((ks[e] + k_a) + k_b) * p.four_pi2;
     };
 
+    // check_alias mask of this thread's outputs (k^2 > k2_cutoff * k2_max, simulation_object.rs:1259-1280): one bit per
+    // output slot, once per tile while registers are free -- the same for every stream of the group
+    unsigned amask = 0u;
+    if constexpr (sop_is_alias(SOP)) {
+#pragma unroll
+        for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+            for (int k = 0; k < RL; ++k) {
+                if (lv && k2_of(t + NT * c + LL * k) > p.alias_k2_thresh) amask |= 1u << (c * RL + k);
+            }
+        }
+    }
     if constexpr (SOP == S_POISSON_INV) {
         // c / (k^2 n^d) of this thread's 8 outputs, once per tile and while registers are free; parked in the stash
 #pragma unroll
@@ -531,6 +573,16 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
         double2* __restrict__ dst = p.dst + (long long)(p.dst_by_sid ? s : li) * p.dst_sstride + base;
         double2* __restrict__ pb = p.pbuf + (p.p_summed ? 0 : (long long)g * p.p_gstride);
         double2* __restrict__ pbl = pb + base;
+        const double2* dt = dts;   // this item's drift factors in shared memory
+        if constexpr (uses_dtab(LOP, SOP)) {
+            const bool resident = p.gsz <= 2;   // both streams of the group stay in their slots for all tiles
+            if (resident) dt = dts + q * N;
+            if (!resident || ti == 0) {
+                if (!resident) __syncthreads();   // the previous item still reads slot 0
+                for (int i = threadIdx.x; i < N; i += THREADS) const_cast<double2*>(dt)[i] = __ldg(&p.dtab[(long long)s * N + i]);
+                __syncthreads();
+            }
+        }
 
         // pull the NEXT item (partner stream of this tile, else first stream of the next tile) into L2 now, so its
         // loads find the data on chip: DRAM stays busy while this item computes
@@ -539,13 +591,14 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             const int nli = same_tile ? li + 1 : g * p.gsz;
             if (same_tile || (tile + 1 < p.ntiles && ti + 1 < p.tiles_per_cta)) {
                 const int ns_ = p.sid[nli];
-                const long long norigin = same_tile ? origin : origin + p.inner_stride;
+                const int norigin = same_tile ? origin : origin + tstride;
                 prefetch_tile(p.src + (long long)(p.src_by_sid ? ns_ : nli) * p.src_sstride + norigin);
                 if ((LOP == L_KICK || LOP == L_KICK_IX) && !same_tile) prefetch_tile(pb + norigin);
             }
         }
 
         double2 v[E];
+        a0v = a0;
         if constexpr (LOP == L_KICK_IX) {
             // last inverse pass of the Poisson solve on this tile of the pair buffer, once per unit; phi_a is parked in
             // the (still idle) exchange buffer, phi_b in the stash, each thread in its own slots
@@ -582,7 +635,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
 #pragma unroll
                 for (int n = 0; n < R0; ++n) {
                     const int e = n * M0 + t + NT * c;
-                    const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
+                    const double2 w = dt[e];
                     v[c * R0 + n] = cmul(v[c * R0 + n], w);
                 }
             }
@@ -640,6 +693,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
         }
 
         // ---- store (last-stage output order) ----
+        fresh_offsets(v[0].x);
         double acc = 0.0, acc2 = 0.0;
 #pragma unroll
         for (int c = 0; c < NBL; ++c) {
@@ -653,12 +707,16 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
                     x.y *= p.scale;
                 }
                 if constexpr (SOP == S_DRIFT || sop_is_alias(SOP)) {
-                    const double2 w = __ldg(&p.dtab[(long long)s * N + e]);
+                    const double2 w = dt[e];
                     x = cmul(x, w);
                 }
                 if constexpr (sop_is_alias(SOP)) {
                     // check_alias: sum |psi_k|^2 where k^2 > k2_cutoff * k2_max  (simulation_object.rs:1259-1280)
+#ifdef MSM_NO_AMASK
                     if (lv && k2_of(e) > p.alias_k2_thresh) acc += x.x * x.x + x.y * x.y;
+#else
+                    if (amask & (1u << (c * RL + k))) acc += x.x * x.x + x.y * x.y;
+#endif
                 }
                 if constexpr (SOP == S_POISSON) {
                     // phi_k = c rho_k / k^2, 0/0 at k = 0 replaced by 0  (simulation_object.rs:1076-1102)
@@ -684,16 +742,16 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
                     } else {
                         const double sum = (q == 0) ? rho : *slot + rho;
                         if (!last_of_group) *slot = sum;
-                        else pair = make_double2(p.rho_accumulate ? pbl[off].x + sum : sum, 0.0);
+                        else pair = make_double2(p.rho_accumulate ? pbl[off].x + sum : sum, 0.0);   // (stored by lv lines only)
                     }
                     if (SOP != S_RHO_ONLY && SOP != S_RHO_ONLY_FX) {
-                        if (lv) dst[off] = x;
+                        dst[off] = x;
                     }
                     if (FX) v[c * RL + k] = pair;               // transformed below, after psi has been stored
                     else if (last_of_group && lv) pbl[off] = pair;
                 }
                 if constexpr (!sop_is_rho(SOP) && SOP != S_MAX) {
-                    if (lv) dst[off] = x;
+                    dst[off] = x;
                 }
                 if constexpr (SOP == S_DRIFT_ALIAS_IZ) v[c * RL + k] = x;   // psi_k as stored; transformed back below
             }
@@ -704,11 +762,12 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             if (last_of_group) {
                 outputs_to_inputs<N>(v);
                 run_stages<N, false, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
+                fresh_offsets(v[0].x);
 #pragma unroll
                 for (int c = 0; c < NBL; ++c) {
 #pragma unroll
                     for (int k = 0; k < RL; ++k) {
-                        if (lv) pbl[eoff(c + k * NBL)] = v[c * RL + k];
+                        pbl[eoff(c + k * NBL)] = v[c * RL + k];
                     }
                 }
             }
@@ -718,11 +777,12 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             double2* __restrict__ d2 = p.dst2 + (long long)li * p.dst_sstride + base;
             outputs_to_inputs<N>(v);
             run_stages<N, true, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
+            fresh_offsets(v[0].x);
 #pragma unroll
             for (int c = 0; c < NBL; ++c) {
 #pragma unroll
                 for (int k = 0; k < RL; ++k) {
-                    if (lv) d2[eoff(c + k * NBL)] = v[c * RL + k];
+                    d2[eoff(c + k * NBL)] = v[c * RL + k];
                 }
             }
         }
@@ -752,6 +812,14 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
             }
         }
     }
+    // All stores of this tile must have left the register file before the next tile's prologue runs.  Without this
+    // fence the LAST 128-bit stores of a tile were seen (CUDA 12.9 ptxas, sm_100a) to pick up register contents written
+    // by the first instructions of the next prologue (LDC / multiplier set-up) -- on non-final tiles of a CTA only,
+    // 1e-6-relative garbage in the low word at N = 1024, wrong Poisson outputs at N = 64; tiles_per_cta = 1 or this
+    // fence make the results exact again (tests: test_fft_matches_pocketfft[1024-2], blocked-layout 64^3 trajectories).
+#ifndef MSM_NO_TILE_FENCE
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
     }   // tiles of this CTA
 
     if constexpr (SOP == S_MAX) {

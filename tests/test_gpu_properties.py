@@ -67,6 +67,45 @@ def test_step_properties_at_full_size(size):
     ctx.close()
 
 
+@pytest.mark.parametrize("size,streams", [(512, 3), (256, 5), (64, 3), (1024, 0)])
+def test_fused_step_equals_the_plain_pass_sequence(monkeypatch, size, streams):
+    """The fused kernels (two transforms per tile, several tiles per CTA) against the un-fused 3+3 pass sequence of the
+    same library (MSM_B200_FUSE=0), whose plain passes are pinned to pocketfft by the FFT tests: two real steps, odd
+    stream count (a group with a single stream).  Caught a store/prologue hazard at tile boundaries (fft_pass.cuh)."""
+    if size == 1024:                                    # 2-D: the only shape at which 1024-point lines are affordable
+        rng = np.random.default_rng(3)
+        a = rng.standard_normal((5, 1024, 1024)) + 1j * rng.standard_normal((5, 1024, 1024))
+        import scipy.fft as sf
+        assert rel_l2(m.forward(a, 2), sf.fftn(a, axes=(1, 2), norm="ortho")) < 1e-13
+        return
+    p = gaussian_params(size)
+    osim = o.SimulationObject(p, np.zeros((2, 2, 2), dtype=np.complex128))
+    results = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("MSM_B200_FUSE", fuse)
+        ctx = m.Context(3, size, streams, p.dx, osim.density_prefactor(), osim.poisson_coeff(), p.k2_cutoff, chunk_streams=4)
+        ctx.ic_cold_gauss(0, [15.0] * 3, [6.0 + streams] * 3)
+        for s in range(1, streams):
+            ctx.ic_copy(s, 0)
+        for s in range(streams):
+            ctx.sample_perturbation(s, "Wigner", 21 + s, 1e6)
+        out = []
+        for step in range(2):
+            pm = ctx.potential_max()
+            dt = p.cfl * np.pi * p.hbar_ / pm * (1.0 + 0.1 * np.arange(streams))     # a different dt per stream
+            alias = ctx.step(dt * p.hbar_ / 4.0, dt / p.hbar_)
+            out.append((pm, alias))
+        out.append([ctx.get_psik(s) for s in (0, streams - 1)])
+        results.append(out)
+        ctx.close()
+    fused, plain = results
+    for step in range(2):
+        assert np.all(np.abs(fused[step][0] - plain[step][0]) <= 1e-12 * plain[step][0])         # max|phi|
+        assert np.all(np.abs(fused[step][1] - plain[step][1]) <= 1e-10 * plain[step][1] + 1e-30)  # alias mass
+    for a, b in zip(fused[2], plain[2]):
+        assert rel_l2(a, b) < 1e-12
+
+
 def test_streams_do_not_leak_into_each_other_256():
     """Two streams share one complex pair buffer for rho/phi; a stream's result must not depend on its partner."""
     p = gaussian_params(256)
