@@ -101,6 +101,9 @@ extern "C" {
     pub fn msm_sim_ctx(sim: *mut MsmSim) -> *mut MsmCtx;
     pub fn msm_sim_set_psi(sim: *mut MsmSim, stream: i32, psi_interleaved: *const f64) -> c_int;
     pub fn msm_sim_update(sim: *mut MsmSim) -> c_int;
+    pub fn msm_sim_update_streams(sim: *mut MsmSim, subset: *const i32) -> c_int;
+    pub fn msm_sim_run_streams(sim: *mut MsmSim, n: i32, streams: *const i32, psi_in: *const *const f64,
+                               re_out: *const *mut f64, im_out: *const *mut f64, max_updates: u64) -> c_int;
     pub fn msm_sim_not_finished(sim: *const MsmSim) -> c_int;
     pub fn msm_sim_state(sim: *const MsmSim, stream: i32, out: *mut MsmStreamState) -> c_int;
     pub fn msm_sim_get_psi(sim: *mut MsmSim, stream: i32, re: *mut f64, im: *mut f64) -> c_int;
@@ -157,6 +160,19 @@ impl B200Simulation {
     /// One `update()` (simulation_object.rs:475 / :669) for every unfinished stream.
     pub fn update(&mut self) -> Result<(), RuntimeError> {
         self.check(unsafe { msm_sim_update(self.raw) })
+    }
+
+    /// The stream loop of simulator/src/main.rs:43-85 in one call: upload `ics[i]` as stream i, `while not_finished()
+    /// { update() }`, final psi into `re[i]` / `im[i]`.  Transfers of neighbouring stream groups overlap the step kernels
+    /// (pin the vectors with cudaHostRegister for the overlap).
+    pub fn run_streams(&mut self, ics: &[Vec<Complex<f64>>], re: &mut [Vec<f64>], im: &mut [Vec<f64>]) -> Result<(), RuntimeError> {
+        let n = ics.len();
+        assert!(re.len() == n && im.len() == n);
+        let ids: Vec<i32> = (0..n as i32).collect();
+        let ins: Vec<*const f64> = ics.iter().map(|v| { assert_eq!(v.len(), self.cells); v.as_ptr() as *const f64 }).collect();
+        let rp: Vec<*mut f64> = re.iter_mut().map(|v| { v.resize(self.cells, 0.0); v.as_mut_ptr() }).collect();
+        let ip: Vec<*mut f64> = im.iter_mut().map(|v| { v.resize(self.cells, 0.0); v.as_mut_ptr() }).collect();
+        self.check(unsafe { msm_sim_run_streams(self.raw, n as i32, ids.as_ptr(), ins.as_ptr(), rp.as_ptr(), ip.as_ptr(), 0) })
     }
 
     /// simulation_object.rs:1226-1228, over all streams.

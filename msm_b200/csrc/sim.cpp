@@ -464,11 +464,25 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
     if (n == 0) return MSM_OK;
     int32_t chunk = 1;
     msm_chunk_streams(sim->ctx, &chunk);
-    // group size: the launch chunk when there are enough streams to pipeline (>= 4 groups), else smaller (even) groups
-    int g = chunk;
-    if (n < 4 * g) g = std::max(2, (n / 4) & ~1);
-    g = std::max(1, std::min(g, (int)chunk));
-    const int ngroups = (n + g - 1) / g;
+    // Groups: the launch chunk when there are enough streams to pipeline, else smaller (even) groups.  The first and
+    // the last group are short (2 streams) so that the un-overlapped upload of the first group and download of the last
+    // one are short: [2, chunk-2, chunk, ..., chunk, chunk-2, 2].
+    std::vector<int> bounds{0};
+    if (n >= 4 * chunk && chunk >= 4) {
+        const int lead[2] = {2, chunk - 2};
+        for (int k = 0; k < 2; ++k) bounds.push_back(bounds.back() + lead[k]);
+        const int tail_begin = n - chunk;
+        while (bounds.back() + chunk <= tail_begin) bounds.push_back(bounds.back() + chunk);
+        if (bounds.back() < tail_begin) bounds.push_back(tail_begin);
+        bounds.push_back(n - 2);
+        bounds.push_back(n);
+    } else {
+        int g = chunk;
+        if (n < 4 * g) g = std::max(2, (n / 4) & ~1);
+        g = std::max(1, std::min(g, (int)chunk));
+        while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + g));
+    }
+    const int ngroups = (int)bounds.size() - 1;
     auto has_out = [&](int i) { return (re_out && re_out[i]) || (im_out && im_out[i]); };
     auto gfail = [&](int rc) {
         sim->err = msm_last_error(sim->ctx);
@@ -476,7 +490,7 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
         return rc;
     };
     auto upload_group = [&](int c) -> int {
-        for (int i = c * g; i < std::min(n, (c + 1) * g); ++i) {
+        for (int i = bounds[c]; i < bounds[c + 1]; ++i) {
             if (!psi_in || !psi_in[i]) continue;
             Stream fresh;                                                        // a new SimulationObject (:404-449)
             fresh.time = p.time;
@@ -504,7 +518,7 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
     for (int c = 0; c < ngroups; ++c) {
         if (c + 1 < ngroups && (rc = upload_group(c + 1))) return gfail(rc);
         std::vector<int32_t> mask(S, 0);
-        const int lo = c * g, hi = std::min(n, (c + 1) * g);
+        const int lo = bounds[c], hi = bounds[c + 1];
         // downloads of the previous group per update of this one (all of them when this group has nothing to do)
         const size_t left = pending.size() - pending_pos;
         const size_t per_update = max_updates ? (left + max_updates - 1) / max_updates : 1;
