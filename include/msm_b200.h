@@ -159,7 +159,9 @@ int msm_spec_grid(int32_t device, int32_t dims, int32_t size, double dx, double*
 
 /* On-device initial conditions (restates simulator/src/ics.rs).  `msm_ic_*` overwrite
  * psi of one stream; msm_sample_perturbation applies `sample_quantum_perturbation` (ics.rs:434-648) with a
- * counter-based Philox-4x32-10 keyed (seed, cell) + Box-Muller (not ArrayFire's stream: unpinned). */
+ * counter-based Philox-4x32-10 keyed (seed, cell): Box-Muller normals for Wigner / Husimi (not ArrayFire's stream:
+ * unpinned), Knuth / PTRS Poisson variates for the Poisson scheme (the reference's own draw is unseeded, ics.rs:497,
+ * so only its distribution can be matched). */
 int msm_ic_cold_gauss(msm_ctx* ctx, int32_t stream, const double* mean, const double* std);
 int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t stream, double axis_length, double radius, double delta,
                             double slope);
@@ -273,6 +275,9 @@ int msm_sim_update_streams(msm_sim* sim, const int32_t* subset);
  * MSM_E_ALIASING after finishing the others.  Independent coupling only. */
 int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const double* const* psi_in,
                         double* const* re_out, double* const* im_out, uint64_t max_updates);
+/* The stream groups msm_sim_run_streams forms for n streams with the given launch chunk: writes the group boundaries
+ * (groups + 1 entries, bounds[0] = 0, last = n; at most cap entries) and returns the number of groups.  Host logic only. */
+int msm_run_groups(int32_t n, int32_t chunk, int32_t* bounds, int32_t cap);
 int msm_sim_not_finished(const msm_sim* sim);                        /* 1 while any stream has time < final    */
 int msm_sim_state(const msm_sim* sim, int32_t stream, msm_stream_state* out);
 int msm_sim_get_psi(msm_sim* sim, int32_t stream, double* re, double* im);

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "msm_sim_update": (C.c_int, [_vp]),
     "msm_sim_update_streams": (C.c_int, [_vp, _ip]),
     "msm_sim_run_streams": (C.c_int, [_vp, C.c_int32, _ip, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.c_uint64]),
+    "msm_run_groups": (C.c_int, [C.c_int32, C.c_int32, _ip, C.c_int32]),
     "msm_sim_not_finished": (C.c_int, [_vp]),
     "msm_sim_state": (C.c_int, [_vp, C.c_int32, C.POINTER(MsmStreamState)]),
     "msm_sim_get_psi": (C.c_int, [_vp, C.c_int32, _dp, _dp]),

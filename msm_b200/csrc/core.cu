@@ -289,6 +289,60 @@ __global__ void k_sample_gauss(double2* __restrict__ psi, long long cells, uint6
         psi[b] = v;
     }
 }
+// sample_quantum_perturbation, Poisson scheme (ics.rs:495-558): |psi| <- sqrt(Pois(|psi|^2 dV n_tot) / n_tot) / sqrt(dV),
+// phase kept.  The reference draws from the unseeded thread_rng (rand_distr 0.4.3), so only the distribution can be
+// matched: counter-based Philox keyed (seed, cell), draw slots 16, 17, ...; Knuth's product method for lambda < 10,
+// Hoermann's PTRS transformed rejection above.
+__device__ __forceinline__ void philox_pair(long long q, uint64_t seed, uint32_t draw, double* u1, double* u2) {
+    uint32_t c0 = (uint32_t)q, c1 = (uint32_t)((uint64_t)q >> 32), c2 = draw, c3 = 0u;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    *u1 = u53(c0, c1);
+    *u2 = u53(c2, c3);
+}
+__device__ double poisson_variate(double lam, long long q, uint64_t seed) {
+    uint32_t draw = 16u;
+    double u1, u2;
+    if (!(lam > 0.0)) return 0.0;
+    if (lam < 10.0) {
+        const double limit = exp(-lam);
+        double prod = 1.0, k = -1.0;
+        for (;;) {
+            philox_pair(q, seed, draw++, &u1, &u2);
+            prod *= u1;
+            k += 1.0;
+            if (!(prod > limit)) return k;
+            prod *= u2;
+            k += 1.0;
+            if (!(prod > limit)) return k;
+        }
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        philox_pair(q, seed, draw++, &u1, &u2);
+        const double U = u1 - 0.5, us = 0.5 - fabs(U);
+        const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && u2 <= vr) return k;
+        if (k < 0.0 || (us < 0.013 && u2 > us)) continue;
+        if (log(u2) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+    }
+}
+__global__ void k_sample_poisson(double2* __restrict__ psi, long long cells, uint64_t seed, double dv, double n_tot, int n,
+                                 int lb) {
+    const double sqrt_dv = sqrt(dv);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < cells; q += (long long)gridDim.x * blockDim.x) {
+        const long long b = blk_index(q, n, lb);
+        const double2 v = psi[b];
+        const double norm2 = v.x * v.x + v.y * v.y;
+        const double count = poisson_variate(norm2 * dv * n_tot, q, seed);     // ics.rs:509-519
+        const double mag = sqrt(count / n_tot);                                 // :523
+        // exp(i arg(psi)) (:535-544); arg(0) = 0
+        const double r = sqrt(norm2);
+        const double cs = r > 0.0 ? v.x / r : 1.0, sn = r > 0.0 ? v.y / r : 0.0;
+        psi[b] = make_double2(mag * cs / sqrt_dv, mag * sn / sqrt_dv);          // :547-557
+    }
+}
 }  // namespace msm
 
 using namespace msm;
@@ -1677,10 +1731,19 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_sample_perturbation: bad argument");
     if (!ctx->has_psi[s] || ctx->in_k[s]) return fail(ctx, MSM_E_STATE, "msm_sample_perturbation: psi must be freshly set");
     if (scheme == MSM_SCHEME_NONE) return MSM_OK;
-    if (scheme != MSM_SCHEME_WIGNER && scheme != MSM_SCHEME_HUSIMI)
-        return fail(ctx, MSM_E_ARG, "only the Wigner and Husimi schemes are implemented on device "
-                                    "(the reference's Poisson scheme is unseeded, ics.rs:497)");
+    if (scheme != MSM_SCHEME_WIGNER && scheme != MSM_SCHEME_HUSIMI && scheme != MSM_SCHEME_POISSON)
+        return fail(ctx, MSM_E_ARG, "unknown sampling scheme");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (scheme == MSM_SCHEME_POISSON) {   // ics.rs:495-558; statistically the reference's sampler (its rng is unseeded, :497)
+        if (!(n_tot > 0.0)) return fail(ctx, MSM_E_ARG, "msm_sample_perturbation: n_tot must be positive");
+        ctx->pmax_valid[s] = 0;
+        if (int rc = wait_upload(ctx, s)) return rc;
+        k_sample_poisson<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed,
+                                                                pow(ctx->cfg.dx, (double)ctx->dims), n_tot, ctx->n, ctx->lb);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return MSM_OK;
+    }
     const double sqrt_dv = sqrt(pow(ctx->cfg.dx, (double)ctx->dims));
     const double div = sqrt(n_tot) * (scheme == MSM_SCHEME_WIGNER ? 2.0 : sqrt(2.0));   // ics.rs:581 / :625
     ctx->pmax_valid[s] = 0;

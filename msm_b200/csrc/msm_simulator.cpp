@@ -9,7 +9,7 @@
 //   dims size axis_length final_sim_time cfl num_data_dumps total_mass particle_mass hbar_ k2_cutoff alias_threshold
 //   sim_name [expanding omega_matter_now omega_radiation_now h z0 max_dloga]
 //   ics = ColdGauss m0 m1 m2 s0 s1 s2 | SphericalTophat radius delta slope | File <raw f64 interleaved, linear layout>
-//   seeds = 1,2,3 (sampled streams "<sim>-stream%05d", then the un-sampled run "<sim>")   scheme = Wigner | Husimi
+//   seeds = 1,2,3 (sampled streams "<sim>-stream%05d", then the un-sampled run "<sim>")   scheme = Wigner | Husimi | Poisson
 // Everything that touches the grid goes through include/msm_b200.h; there is no other dependency.
 #include <stdio.h>
 #include <stdlib.h>
@@ -180,7 +180,8 @@ int main(int argc, char** argv) {
     }
     for (int s = 1; s < S; ++s) CHECK_CTX(msm_ic_copy(ctx, s, 0));
     const std::string scheme = kv.count("scheme") ? kv.at("scheme") : "";
-    const int scheme_id = scheme == "Wigner" ? MSM_SCHEME_WIGNER : scheme == "Husimi" ? MSM_SCHEME_HUSIMI : MSM_SCHEME_NONE;
+    const int scheme_id = scheme == "Wigner" ? MSM_SCHEME_WIGNER : scheme == "Husimi" ? MSM_SCHEME_HUSIMI
+                          : scheme == "Poisson" ? MSM_SCHEME_POISSON : MSM_SCHEME_NONE;
     const double n_tot = p.total_mass / p.particle_mass;
     for (size_t i = 0; i < seeds.size(); ++i)
         if (scheme_id != MSM_SCHEME_NONE) CHECK_CTX(msm_sample_perturbation(ctx, (int)i, scheme_id, (uint64_t)seeds[i], n_tot));

@@ -188,6 +188,30 @@ bool write_npy(const std::string& path, const double* data, int dims, int n) {
     return ok;
 }
 
+// Stream groups of msm_sim_run_streams: the launch chunk when there are enough streams to pipeline, else smaller
+// (even) groups.  The first and the last group are short (2 streams) so that the un-overlapped upload of the first
+// group and download of the last one are short: [2, chunk-2, chunk, ..., chunk, chunk-2, 2].
+std::vector<int> run_groups(int n, int chunk) {
+    std::vector<int> bounds{0};
+    if (n <= 0) return bounds;
+    chunk = std::max(1, chunk);
+    if (n >= 4 * chunk && chunk >= 4) {
+        const int lead[2] = {2, chunk - 2};
+        for (int k = 0; k < 2; ++k) bounds.push_back(bounds.back() + lead[k]);
+        const int tail_begin = n - chunk;
+        while (bounds.back() + chunk <= tail_begin) bounds.push_back(bounds.back() + chunk);
+        if (bounds.back() < tail_begin) bounds.push_back(tail_begin);
+        bounds.push_back(n - 2);
+        bounds.push_back(n);
+    } else {
+        int g = chunk;
+        if (n < 4 * g) g = std::max(2, (n / 4) & ~1);
+        g = std::max(1, std::min(g, chunk));
+        while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + g));
+    }
+    return bounds;
+}
+
 void mkdirs(const std::string& path) {
     std::string cur;
     for (size_t i = 0; i < path.size(); ++i) {
@@ -435,6 +459,13 @@ int msm_sim_update(msm_sim* sim) {
     return update_streams(sim, nullptr);
 }
 
+int msm_run_groups(int32_t n, int32_t chunk, int32_t* bounds, int32_t cap) {
+    const std::vector<int> b = run_groups(n, chunk);
+    if (bounds)
+        for (size_t i = 0; i < b.size() && (int32_t)i < cap; ++i) bounds[i] = b[i];
+    return (int)b.size() - 1;
+}
+
 int msm_sim_update_streams(msm_sim* sim, const int32_t* subset) {
     if (!sim) return MSM_E_ARG;
     if (subset && sim->p.coupling == MSM_COUPLING_SUMMED)
@@ -464,24 +495,7 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
     if (n == 0) return MSM_OK;
     int32_t chunk = 1;
     msm_chunk_streams(sim->ctx, &chunk);
-    // Groups: the launch chunk when there are enough streams to pipeline, else smaller (even) groups.  The first and
-    // the last group are short (2 streams) so that the un-overlapped upload of the first group and download of the last
-    // one are short: [2, chunk-2, chunk, ..., chunk, chunk-2, 2].
-    std::vector<int> bounds{0};
-    if (n >= 4 * chunk && chunk >= 4) {
-        const int lead[2] = {2, chunk - 2};
-        for (int k = 0; k < 2; ++k) bounds.push_back(bounds.back() + lead[k]);
-        const int tail_begin = n - chunk;
-        while (bounds.back() + chunk <= tail_begin) bounds.push_back(bounds.back() + chunk);
-        if (bounds.back() < tail_begin) bounds.push_back(tail_begin);
-        bounds.push_back(n - 2);
-        bounds.push_back(n);
-    } else {
-        int g = chunk;
-        if (n < 4 * g) g = std::max(2, (n / 4) & ~1);
-        g = std::max(1, std::min(g, (int)chunk));
-        while (bounds.back() < n) bounds.push_back(std::min(n, bounds.back() + g));
-    }
+    const std::vector<int> bounds = run_groups(n, chunk);
     const int ngroups = (int)bounds.size() - 1;
     auto has_out = [&](int i) { return (re_out && re_out[i]) || (im_out && im_out[i]); };
     auto gfail = [&](int rc) {

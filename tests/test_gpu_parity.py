@@ -467,6 +467,46 @@ def test_device_initial_conditions_match_oracle():
     ctx.close()
 
 
+def test_device_poisson_sampling_scheme_statistics():
+    """ics.rs:495-558: |psi| <- sqrt(Pois(|psi|^2 dV n_tot) / n_tot), phase kept.  The reference's draw is unseeded
+    (thread_rng), so the check is distributional: mean and variance of the counts equal lambda (both branches of the
+    generator: product method below 10, PTRS above), phases survive, seeds decorrelate, empty cells stay empty."""
+    p = oracle_streams("spherical-tophat", 32, limit=1)[0]
+    dv, cells = p.dx ** 3, 32 ** 3
+    rng = np.random.default_rng(3)
+    phase = np.exp(2j * np.pi * rng.random((32, 32, 32)))
+    for lam in (0.4, 6.0, 35.0, 4.0e4, 3.0e9):
+        n_tot = 1.0e12
+        amp = np.sqrt(lam / (dv * n_tot))
+        psi0 = amp * phase
+        psi0[0, 0, :4] = 0.0                                       # empty cells
+        ctx = make_ctx(p, 2)
+        ctx.set_psi(0, psi0)
+        ctx.set_psi(1, psi0)
+        ctx.sample_perturbation(0, "Poisson", 11, n_tot)
+        ctx.sample_perturbation(1, "Poisson", 12, n_tot)
+        a, b = ctx.get_psi(0), ctx.get_psi(1)
+        ctx.close()
+        counts = np.abs(a) ** 2 * dv * n_tot
+        assert np.all(counts[0, 0, :4] == 0.0)
+        live = np.ones(counts.shape, bool)
+        live[0, 0, :4] = False
+        c = counts[live]
+        assert np.allclose(c, np.rint(c), rtol=0, atol=1e-6 * max(1.0, lam))             # integer counts
+        assert abs(c.mean() - lam) < 6.0 * np.sqrt(lam / c.size)
+        assert abs(c.var() - lam) < 6.0 * lam * np.sqrt(2.0 / c.size) + 6.0 * np.sqrt(lam / c.size)
+        nz = live & (counts > 0)
+        assert np.max(np.abs(a[nz] / np.abs(a[nz]) - phase[nz])) < 1e-12                 # phases kept
+        cb = (np.abs(b) ** 2 * dv * n_tot)[live]
+        assert abs(np.corrcoef(c, cb)[0, 1]) < 6.0 / np.sqrt(c.size)                     # another seed, another draw
+    # same seed -> same field, on any chunking
+    ctx = make_ctx(p, 1)
+    ctx.set_psi(0, psi0)
+    ctx.sample_perturbation(0, "Poisson", 11, n_tot)
+    assert np.array_equal(ctx.get_psi(0), a)
+    ctx.close()
+
+
 def test_error_behaviour():
     p = oracle_streams("spherical-tophat", limit=1)[0]
     ctx = make_ctx(p, 2)

@@ -143,3 +143,24 @@ def test_reference_arm_of_bench_runs_on_cpu():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "cell-updates/s"
+
+
+@pytest.mark.parametrize("n,chunk", [(64, 8), (8, 8), (1, 2), (3, 2), (11, 2), (16, 4), (17, 4), (33, 8), (5, 6), (100, 16), (2, 8)])
+def test_run_streams_group_schedule(n, chunk):
+    """Stream groups of msm_sim_run_streams (the pipelined outer loop of main.rs:43-85): a partition of the stream list
+    in order, no group larger than the launch chunk, pairs never split (even group sizes except a ragged last piece),
+    and short first / last groups when there is something to overlap them with."""
+    import ctypes as C
+    from msm_b200._lib import lib
+    buf = (C.c_int32 * 128)()
+    g = lib.msm_run_groups(n, chunk, buf, 128)
+    b = list(buf[:g + 1])
+    sizes = [b[i + 1] - b[i] for i in range(g)]
+    assert b[0] == 0 and b[-1] == n and all(s > 0 for s in sizes) and max(sizes) <= max(chunk, 2)
+    assert all(s % 2 == 0 for s in sizes[:-1]) or n % 2 == 1
+    starts_even = all(x % 2 == 0 for x in b[:-1]) or n % 2 == 1
+    assert starts_even
+    if n >= 4 * chunk and chunk >= 4:
+        assert sizes[0] == 2 and sizes[-1] == 2 and sizes[1] == chunk - 2
+    if n >= 8:
+        assert g >= 4                                             # enough groups to overlap transfers with compute
