@@ -112,7 +112,10 @@ MSM_PLAN(256,  8, 8,  2, 3, 4, 8, 8, 1)
 #ifndef MSM_MINB512
 #define MSM_MINB512 2
 #endif
-MSM_PLAN(512,  8, 8,  MSM_MINB512, 3, 8, 8, 8, 1)
+#ifndef MSM_E512
+#define MSM_E512 8
+#endif
+MSM_PLAN(512,  MSM_E512, 8,  MSM_MINB512, 3, 8, 8, 8, 1)
 MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #undef MSM_PLAN
 
@@ -494,11 +497,17 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     // CUDA 12.9 ptxas for sm_100a: the one `@!P STG.128` it formed from `if (lv) *o = x` at the end of the item body lost
     // the low word of its data to the next tile's prologue (LDC into the same register).
     const int la = lv ? l : 0;
-    // L2 prefetch of one tile, one 128-byte line per thread (THREADS == N on the strided axes: one line per position;
-    // contiguous axis: the tile is T * N * 16 = THREADS * 128 contiguous bytes)
+    // L2 prefetch of one tile: 128-byte lines, thread `tid` takes lines tid, tid + THREADS, ... (strided axes: one line per
+    // position, N of them; contiguous axis: the tile is T * N * 16 contiguous bytes = N * T / 8 lines)
+    constexpr int PF_LINES = XL ? (N * T) / 8 : N;
+    constexpr int PF_ITERS = (PF_LINES + THREADS - 1) / THREADS;
     const int pf_off = XL ? tid * 8 : (int)along(tid < N ? tid : 0);
+    const int pf_step = XL ? THREADS * 8 : (int)((long long)(THREADS >> p.alb) * p.astride);
     auto prefetch_tile = [&](const double2* arr_at_origin) {
-        if (XL ? tid < (N * T) / 8 : tid < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(arr_at_origin + pf_off));
+#pragma unroll
+        for (int i = 0; i < PF_ITERS; ++i)
+            if (tid + i * THREADS < PF_LINES)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(arr_at_origin + pf_off + i * pf_step));
     };
 
     // the host makes tiles_per_cta a divisor of tiles_inner: consecutive tiles of one CTA differ by inner_stride
