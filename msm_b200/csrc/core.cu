@@ -887,7 +887,8 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;
     // the pass kernels address a thread's elements e = t + NT * j (NT = n / 8 threads per line) as a0 + j * step,
     // which needs NT to be a multiple of the block
-    while (ctx->lb > 0 && (n < 16 || (n / 8) % (1 << ctx->lb))) ctx->lb--;
+    // (n / 16 at n = 512, where one kernel runs 16 points per thread: fft_pass.cuh plan_E)
+    while (ctx->lb > 0 && (n < 16 || ((n == 512 ? n / 16 : n / 8) % (1 << ctx->lb)))) ctx->lb--;
     ctx->num_sms = prop.multiProcessorCount;
     int chunk = cfg->chunk_streams > 0 ? cfg->chunk_streams : 8;
     chunk = std::min(chunk, MAX_CHUNK);

@@ -33,7 +33,7 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
         cudaFuncAttributes fa;
         int pct = (int)cudaSharedmemCarveoutDefault;
         if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
-            const size_t need = (smem + fa.sharedSizeBytes + 1024) * (size_t)tile_minb<N, XL>();
+            const size_t need = (smem + fa.sharedSizeBytes + 1024) * (size_t)tile_minb<N, XL, plan_E<N, LOP, SOP, XL>()>();
             pct = (int)((need * 100 + 227 * 1024 - 1) / (227 * 1024)) + 1;
             if (pct > 100) pct = 100;
         }
@@ -42,7 +42,7 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta, groups, 1);
-    kern<<<grid, tile_threads<N, XL>(), smem, st>>>(p);
+    kern<<<grid, tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>(), smem, st>>>(p);
     return (int)cudaPeekAtLastError();
 }
 

@@ -127,14 +127,24 @@ MSM_PLAN(1024, 8, 8,  1, 4, 2, 8, 8, 8)
 #define MSM_TX 2
 #endif
 template <int N, bool XL> constexpr int tile_T() { return (XL && N >= 256 && Plan<N>::T == 8) ? MSM_TX : Plan<N>::T; }
-template <int N, bool XL> constexpr int tile_threads() { return Plan<N>::NT * tile_T<N, XL>(); }
+template <int N, bool XL, int EV = Plan<N>::E> constexpr int tile_threads() { return (N / EV) * tile_T<N, XL>(); }
 // Resident CTAs the small-tile contiguous-axis kernels are compiled for.  Measured (profiles/README.md): 4 CTAs per SM
 // with 128 registers beat 8 CTAs with 64 (spills, no room to overlap loads with butterflies): +8 % on the whole step.
 #ifndef MSM_XL_MINB
 #define MSM_XL_MINB 4
 #endif
-template <int N, bool XL> constexpr int tile_minb() {
+template <int N, bool XL, int EV = Plan<N>::E> constexpr int tile_minb() {
+    if (EV != Plan<N>::E) return Plan<N>::MINB;   // wide variant: half the threads, the same CTAs, twice the registers
     return (XL && tile_T<N, XL>() != Plan<N>::T) ? MSM_XL_MINB : Plan<N>::MINB * (Plan<N>::T / tile_T<N, XL>());
+}
+// Points per thread of one kernel instance.  E = 8 everywhere (Plan) except where a kernel measured faster with E = 16
+// (half the threads, 128 registers, the same two CTAs per SM): the two-transform strided kernel `drift+alias+inv`, which
+// at 64 registers cannot hold its 8 store addresses per output array next to the butterflies (+12 %, profiles/README.md).
+#ifndef MSM_WIDE_DAI
+#define MSM_WIDE_DAI 1
+#endif
+template <int N, int LOP, int SOP, bool XL> constexpr int plan_E() {
+    return (MSM_WIDE_DAI && N == 512 && !XL && SOP == 11 /* S_DRIFT_ALIAS_IZ */) ? 16 : Plan<N>::E;
 }
 
 template <int N> constexpr int plan_L(int q) {   // product of radices of stages < q
@@ -306,15 +316,15 @@ template <int N, bool XL> __device__ __forceinline__ int sm_index(int pos, int l
 // Exchange barrier.  Contiguous-axis mapping with NT a multiple of 32: the NT threads of one line are whole warps and
 // exchange only among themselves, so each line gets its own named barrier (1 + l) and never waits for the other lines
 // of the tile.  Otherwise the lines are interleaved across all warps: CTA-wide barrier.
-template <int N, bool XL> __device__ __forceinline__ void exchange_barrier(int l) {
-    if constexpr (XL && (Plan<N>::NT % 32 == 0)) {
+template <int N, bool XL, int EV> __device__ __forceinline__ void exchange_barrier(int l) {
+    if constexpr (XL && ((N / EV) % 32 == 0)) {
         // The barrier id must be an IMMEDIATE: with a register operand ptxas cannot tell which barriers the kernel
         // uses and reserves all 16 for every CTA ("used 16 barriers"), and an SM has 64 barrier slots -> 4 CTAs per SM
         // instead of 8 (ncu: 16 resident warps; profiles/README.md).  The branch is warp-uniform (a warp = one line).
         constexpr int T = tile_T<N, true>();
         static_assert(T <= 8, "one named barrier per line");
 #define MSM_LINE_BAR(ID)                                                                      \
-    if (T > ID && l == ID) asm volatile("bar.sync %0, %1;" ::"n"(1 + ID), "n"(Plan<N>::NT) : "memory");
+    if (T > ID && l == ID) asm volatile("bar.sync %0, %1;" ::"n"(1 + ID), "n"(N / EV) : "memory");
         MSM_LINE_BAR(0) MSM_LINE_BAR(1) MSM_LINE_BAR(2) MSM_LINE_BAR(3)
         MSM_LINE_BAR(4) MSM_LINE_BAR(5) MSM_LINE_BAR(6) MSM_LINE_BAR(7)
 #undef MSM_LINE_BAR
@@ -329,11 +339,11 @@ template <int N, bool XL> __device__ __forceinline__ void exchange_barrier(int l
 #define MSM_TW_SMEM 1
 #endif
 constexpr bool kTwSmem = MSM_TW_SMEM != 0;
-template <int N, bool INV, bool XL, int Q>
-__device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm, int t, int l,
+template <int N, bool INV, bool XL, int Q, int EV>
+__device__ __forceinline__ void run_stages(double2 (&v)[EV], double2* sm, int t, int l,
                                            const double2* __restrict__ tw) {
     using PL = Plan<N>;
-    constexpr int E = PL::E, NT = PL::NT;
+    constexpr int E = EV, NT = N / EV;
     constexpr int R = PL::R[Q];
     constexpr int L = plan_L<N>(Q);
     constexpr int M = N / (L * R);
@@ -358,7 +368,7 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
                 sm[sm_index<N, XL>((kappa + L * k) * M + nu, l)] = x;
             }
         }
-        exchange_barrier<N, XL>(l);
+        exchange_barrier<N, XL, EV>(l);
         constexpr int R2 = PL::R[Q + 1];
         constexpr int L2 = L * R;
         constexpr int M2 = N / (L2 * R2);
@@ -370,7 +380,7 @@ __device__ __forceinline__ void run_stages(double2 (&v)[Plan<N>::E], double2* sm
 #pragma unroll
             for (int n = 0; n < R2; ++n) v[c * R2 + n] = sm[sm_index<N, XL>(kappa * (M2 * R2) + n * M2 + nu, l)];
         }
-        exchange_barrier<N, XL>(l);
+        exchange_barrier<N, XL, EV>(l);
         run_stages<N, INV, XL, Q + 1>(v, sm, t, l, tw);
     }
 }
@@ -389,24 +399,24 @@ constexpr bool sop_needs_k2(int sop) { return sop_is_alias(sop) || sop == S_POIS
 // (slot c * R0 + n  <->  m = n * (E / R0) + c) and as outputs of the last stage (slot c * RL + k  <->
 // m = c + (E / RL) * k).  Chaining a second transform on the same lines is therefore a compile-time register
 // permutation, no data exchange.
-template <int N> struct Slots {
+template <int N, int EV> struct Slots {
     using PL = Plan<N>;
-    static constexpr int E = PL::E, R0 = PL::R[0], RL = PL::R[PL::NS - 1];
+    static constexpr int E = EV, R0 = PL::R[0], RL = PL::R[PL::NS - 1];
     static constexpr int in_slot_m(int slot) { return (slot % R0) * (E / R0) + slot / R0; }
     static constexpr int out_slot_of_m(int m) { return (m % (E / RL)) * RL + m / (E / RL); }
     static constexpr bool identity = (R0 == E && RL == E);
 };
-template <int N> __device__ __forceinline__ void outputs_to_inputs(double2 (&v)[Plan<N>::E]) {
-    if constexpr (!Slots<N>::identity) {
-        double2 w[Plan<N>::E];
+template <int N, int EV> __device__ __forceinline__ void outputs_to_inputs(double2 (&v)[EV]) {
+    if constexpr (!Slots<N, EV>::identity) {
+        double2 w[EV];
 #pragma unroll
-        for (int i = 0; i < Plan<N>::E; ++i) w[i] = v[Slots<N>::out_slot_of_m(Slots<N>::in_slot_m(i))];
+        for (int i = 0; i < EV; ++i) w[i] = v[Slots<N, EV>::out_slot_of_m(Slots<N, EV>::in_slot_m(i))];
 #pragma unroll
-        for (int i = 0; i < Plan<N>::E; ++i) v[i] = w[i];
+        for (int i = 0; i < EV; ++i) v[i] = w[i];
     }
 }
 // exchange region in double2 units; single-stage plans (N <= 8) have no exchange, but L_KICK_IX parks phi_a there
-template <int N, int LOP, bool XL> constexpr int exchange_elems() {
+template <int N, int LOP, bool XL> constexpr int exchange_elems() {   // (E * threads = N * T for every E)
     return Plan<N>::NS > 1 ? (XL ? (N + N / 8) : N) * tile_T<N, XL>()
                            : (LOP == L_KICK_IX ? (Plan<N>::E * tile_threads<N, XL>() + 1) / 2 : 0);
 }
@@ -419,15 +429,16 @@ constexpr bool uses_dtab(int lop, int sop) { return lop == L_DRIFT || sop == S_D
 template <int N, int LOP, int SOP> constexpr int table_elems() {   // double2 units
     return (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0) + (uses_dtab(LOP, SOP) ? 2 * N : 0);
 }
-template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {
+template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {   // E * threads = N * T for every E
     return sizeof(double2) * (exchange_elems<N, LOP, XL>() + table_elems<N, LOP, SOP>()) +
            (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * tile_threads<N, XL>() : 0);
 }
 
 template <int N, bool INV, int LOP, int SOP, bool XL>
-__global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft_pass_kernel(const PassParams p) {
+__global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>(),
+                                  tile_minb<N, XL, plan_E<N, LOP, SOP, XL>()>()) fft_pass_kernel(const PassParams p) {
     using PL = Plan<N>;
-    constexpr int E = PL::E, T = tile_T<N, XL>(), NT = PL::NT, THREADS = tile_threads<N, XL>();
+    constexpr int E = plan_E<N, LOP, SOP, XL>(), T = tile_T<N, XL>(), NT = N / E, THREADS = NT * T;
     constexpr int R0 = PL::R[0];
     constexpr int M0 = N / R0;
     constexpr int NB0 = E / R0;
@@ -445,11 +456,11 @@ __global__ void __launch_bounds__(tile_threads<N, XL>(), tile_minb<N, XL>()) fft
     double2* dts = tws + (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0);
     const double2* tw_base = p.twiddle;
     if constexpr (kTwSmem) {
-        for (int i = threadIdx.x; i < N; i += tile_threads<N, XL>()) tws[i] = p.twiddle[i];
+        for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = p.twiddle[i];
         tw_base = tws;
     }
     if constexpr (sop_needs_k2(SOP)) {
-        for (int i = threadIdx.x; i < N; i += tile_threads<N, XL>()) ks[i] = p.ksq[i];
+        for (int i = threadIdx.x; i < N; i += THREADS) ks[i] = p.ksq[i];
     }
     if constexpr (kTwSmem || sop_needs_k2(SOP)) __syncthreads();
     double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
