@@ -9,10 +9,12 @@
 // get_supercomoving_boxsize (common/src/parameters.rs:205-220).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <string>
 #include <thread>
@@ -525,12 +527,22 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
         }
         return MSM_OK;
     };
+    // MSM_B200_TRACE=1: wall-clock milestones of the pipeline on stderr (diagnostics only)
+    const bool trace = getenv("MSM_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what, int c) {
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        fprintf(stderr, "[msm_sim_run_streams] %9.2f ms  %s %d\n", ms, what, c);
+    };
     int result = MSM_OK;
     std::string alias_text;
     int rc = upload_group(0);
+    stamp("uploads enqueued for group", 0);
     if (rc) return gfail(rc);
     for (int c = 0; c < ngroups; ++c) {
         if (c + 1 < ngroups && (rc = upload_group(c + 1))) return gfail(rc);
+        stamp("start of group", c);
         std::vector<int32_t> mask(S, 0);
         const int lo = bounds[c], hi = bounds[c + 1];
         // downloads of the previous group per update of this one (all of them when this group has nothing to do)
@@ -552,8 +564,10 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
                 msm_transfers_wait(sim->ctx);
                 return rc;
             }
+            if (u == 0) stamp("first update done of group", c);
             if ((rc = download_some(per_update))) return gfail(rc);
         }
+        stamp("updates done of group", c);
         if ((rc = download_some(pending.size()))) return gfail(rc);
         pending.clear();
         pending_pos = 0;
@@ -561,7 +575,9 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
             if (has_out(i)) pending.push_back(i);
     }
     if ((rc = download_some(pending.size()))) return gfail(rc);
+    stamp("last downloads enqueued", ngroups);
     if ((rc = msm_transfers_wait(sim->ctx))) return gfail(rc);
+    stamp("transfers done", ngroups);
     if (result == MSM_E_ALIASING) sim->err = alias_text;
     return result;
 }
