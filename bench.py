@@ -163,6 +163,33 @@ def build_streams(sim, n_local, first_global, size):
     g.synchronize()
 
 
+def bind_to_gpu_numa_node(device):
+    """Run this rank on the CPU cores next to its GPU (sysfs local_cpulist of the GPU's PCI function), so that the pinned
+    host buffers of the end-to-end leg are allocated on that NUMA node: with 8 ranks on one box the transfers otherwise
+    all cross the same socket.  Best effort; returns what was done for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"cpus {text} (gpu {bdf})"
+        return f"unchanged ({text or 'no local_cpulist'})"
+    except Exception as e:          # containers without sysfs access, older torch, ...
+        return f"unavailable ({type(e).__name__})"
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -176,8 +203,12 @@ def main():
     import torch.distributed as dist
     import msm_b200 as m
 
+    # (single rank: keep all cores -- the CPU baseline leg below runs on them)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "all cores (single rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout; stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
@@ -345,7 +376,8 @@ def main():
                 "config": {"workload": f"synthetic {size}^3 x {n_total} streams fp64 static box (BASELINE configs[4])",
                            "streams_per_gpu": n_local, "coupling": args.coupling, "chunk_streams": chunk,
                            "l2": "inputs larger than L2 (2 GiB per stream vs 126 MB)",
-                           "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
+                           "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall,
+                           "cpu_affinity": numa},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
