@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
                              "sample": f"1 stream x {size}^3 per step, NumPy/pocketfft restatement of update()"},
             "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def build_streams(sim, n_local, first_global, size):
@@ -190,7 +190,23 @@ def bind_to_gpu_numa_node(device):
         return f"unavailable ({type(e).__name__})"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line on the process's real stdout"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries write banners to stdout at the file-descriptor level (NCCL prints "NCCL version ..." when NCCL_DEBUG is
+    # set): everything but the JSON line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,8 +223,6 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "all cores (single rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout; stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
@@ -379,7 +393,7 @@ def main():
                            "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall,
                            "cpu_affinity": numa},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
