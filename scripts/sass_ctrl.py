@@ -12,24 +12,33 @@ import subprocess
 import sys
 
 
-def kernel_instructions(obj, key):
+def all_kernels(obj):
+    """{mangled name: [instruction dicts]} for every kernel of an object file / cubin (one cuobjdump call)"""
     text = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout.split("\n")
-    out, on, i = [], False, 0
+    kernels, cur, i = {}, None, 0
     while i < len(text):
         line = text[i]
-        if "Function :" in line:
-            on = key in line
-        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);\s+/\* (0x[0-9a-f]+) \*/", line) if on else None
+        f = re.search(r"Function : (\S+)", line)
+        if f:
+            cur = kernels.setdefault(f.group(1), [])
+        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);\s+/\* (0x[0-9a-f]+) \*/", line) if cur is not None else None
         if m and i + 1 < len(text):
             m2 = re.match(r"\s+/\* (0x[0-9a-f]+) \*/", text[i + 1])
             if m2:
                 ctrl = (int(m2.group(1), 16) >> 41) & 0x1FFFFF
-                out.append(dict(addr=m.group(1), text=m.group(2).strip(), stall=ctrl & 0xF, wr=(ctrl >> 5) & 7,
+                cur.append(dict(addr=m.group(1), text=m.group(2).strip(), stall=ctrl & 0xF, wr=(ctrl >> 5) & 7,
                                 rd=(ctrl >> 8) & 7, wait=(ctrl >> 11) & 0x3F))
                 i += 2
                 continue
         i += 1
-    return out
+    return kernels
+
+
+def kernel_instructions(obj, key):
+    for name, ins in all_kernels(obj).items():
+        if key in name:
+            return ins
+    return []
 
 
 if __name__ == "__main__":

@@ -98,3 +98,21 @@ def test_native_host_binary_is_built_and_links_only_the_c_abi():
     assert out.returncode == 2 and "usage" in out.stderr
     needed = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
     assert "libmsm_b200.so" in needed and "torch" not in needed and "python" not in needed
+
+
+def test_no_store_backedge_hazard_in_the_built_kernels():
+    """Static guard for the ptxas problem of DESIGN.md section 6: in the SASS of every built pass kernel, no instruction
+    reached through a loop back-edge overwrites a register that a store before the branch still has to read without a
+    wait for that store's read barrier (or a MEMBAR) in between.  scripts/check_war_hazard.py flags exactly the pattern
+    found in the build without the tile-boundary fence."""
+    import glob
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    objs = sorted(glob.glob(os.path.join(ROOT, "msm_b200", "csrc", "build", "fft_*.o")))
+    if not objs:
+        pytest.skip("no kernel objects (library built elsewhere)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_war_hazard.py")] + objs, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
