@@ -21,7 +21,7 @@ from sass_ctrl import all_kernels  # noqa: E402
 NO_DEST = ("ST", "BRA", "BAR", "EXIT", "ISETP", "DSETP", "FSETP", "MEMBAR", "CCTL", "NOP", "BSYNC", "BSSY", "RED", "PLOP",
            "WARPSYNC", "ERRBAR", "UISETP", "UIADD", "UIMAD", "ULEA", "USHF", "UMOV", "USEL", "ULOP", "UPLOP", "LDCU", "S2UR",
            "R2UR", "UFLO", "UPOPC", "UBREV", "UBMSK", "VOTEU", "UP2UR", "UR2UP", "UCLEA", "UF2FP", "CALL", "RET", "YIELD")
-LOOKBACK, DEPTH = 160, 320
+LOOKBACK, DEPTH = 4000, 1500
 
 
 def strip_pred(text):
