@@ -620,10 +620,16 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
     p.alias_partial = ctx->alias_partial;
     p.maxbits = o.maxbits ? o.maxbits : ctx->maxbits;
     p.dst2 = o.dst2;
-    const int groups = (ns + o.gsz - 1) / o.gsz;
     for (size_t k = 0; k < seq.size(); ++k) {
         const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop;
         const bool inv = seq[k].inv;
+        // Streams per CTA group.  Only passes that touch the pair buffer need the whole group in one CTA (summed
+        // coupling: rho accumulates over / phi is shared by all streams of the group); every other pass runs in pairs, so
+        // that the two drift tables of a CTA stay resident in shared memory (fft_pass.cuh).
+        const bool pair_pass = lop == L_KICK || lop == L_KICK_IX || sop_is_rho(sop) || sop == S_POISSON ||
+                               sop == S_POISSON_INV || sop == S_MAX;
+        p.gsz = pair_pass ? o.gsz : std::min(o.gsz, 2);
+        const int groups = (ns + p.gsz - 1) / p.gsz;
         const Geom g = make_geom(ctx, axis, (axis == 0 && ctx->xl) ? ctx->TX : ctx->T);
         const bool first = (k == 0);
         p.src = first ? src : work;
