@@ -23,6 +23,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def claim_host_cores():
+    """The CPU legs (--impl reference, cpu_baseline) use every host core.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which throttles NumPy's OpenBLAS pool (measured: the same oracle step ran 3x slower under torchrun in
+    round 1), so the thread-count variables are set BEFORE NumPy is imported, and the affinity mask is widened to all
+    cores where the container allows it.  Returns the number of cores this process may run on."""
+    n = os.cpu_count() or 1
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(n)
+    try:
+        os.sched_setaffinity(0, range(n))
+    except (OSError, AttributeError):
+        pass
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return n
+
+
+# rank 0 of the reference arm and the single-rank GPU arm (cpu_baseline leg) run CPU work; GPU ranks under torchrun do not
+HOST_CORES = (claim_host_cores() if ("reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1)
+              else (os.cpu_count() or 1))
+
 import numpy as np  # noqa: E402
 
 ALG_BYTES_PER_CELL_UPDATE = 480.0       # SURVEY 8d / DESIGN.md section 3: 3-pass transforms, un-fused pass boundaries
@@ -133,21 +156,34 @@ def cpu_step_rate(size, steps, warmup):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU algorithm (oracle restatement: the Rust/ArrayFire binary cannot be
-    built here) with all host threads.  Each step = one update() of ONE stream on a bounded grid."""
+    built here) with all host threads.  Each step is a bounded sample of the workload: one update() of ONE of its
+    streams on the workload's own grid (512^3; cell-updates/s is a per-cell rate, so one stream measures it).  If a
+    512^3 step turns out too slow for the --steps/--warmup asked for (more than ~10 minutes in all), the sample drops
+    to 256^3 and the line says so."""
     if rank != 0:
         return
     from oracle import msm_oracle as o
-    cores = os.cpu_count() or 1
-    o.set_workers(cores)
-    size = args.cpu_size or 256
+    o.set_workers(HOST_CORES)
+    size = args.cpu_size or args.size
+    note = ""
+    if not args.cpu_size and size > 256:
+        t0 = time.perf_counter()
+        probe_rate, _ = cpu_step_rate(256, 1, 1)
+        est = (size ** 3 / probe_rate) * (args.steps + args.warmup)
+        if est > 600.0:
+            note = f" (a {size}^3 step would take {size ** 3 / probe_rate:.0f} s: sample reduced to 256^3)"
+            size = 256
     rate, sec = cpu_step_rate(size, args.steps, args.warmup)
+    sample = (f"1 of the {args.streams} streams x {size}^3 per step{note}, NumPy/pocketfft restatement of the "
+              f"reference's un-fused update(), {o.get_workers()} worker threads")
     line = {"impl": "reference", "metric": "cell-updates/s", "value": rate, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic {args.size}^3 x {args.streams} streams fp64 static box (BASELINE configs[4])",
-                       "coupling": args.coupling},
-            "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-                             "sample": f"1 stream x {size}^3 per step, NumPy/pocketfft restatement of update()"},
+                       "coupling": args.coupling, "sample": sample, "sample_grid": size, "sample_streams": 1,
+                       "workers_used": o.get_workers(), "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
+            "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": HOST_CORES, "kind": "port",
+                             "sample": sample},
             "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -321,7 +357,7 @@ def main():
             if k.startswith(key):
                 traffic, traffic_src = v["dram_bytes_per_launch"], "profiles/r01g_ncu_dram_traffic.json"
     roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "traffic_measured_in_run": False,
                 "algorithmic_bytes_per_launch": top["algorithmic_bytes"] / top["launches"], "peak_source": peak_src,
                 "avg_launch_ms": top["ms_total"] / top["launches"], "share_of_step": top["ms_total"] / kernel_ms,
                 "step": {"algorithmic_bytes_per_cell_update": alg_bytes(args.coupling, n_local),
@@ -375,13 +411,13 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import msm_oracle as o
-        cores = os.cpu_count() or 1
-        o.set_workers(cores)
-        csize = args.cpu_size or 256
+        o.set_workers(HOST_CORES)
+        csize = args.cpu_size or size
         rate, sec = cpu_step_rate(csize, 2, 1)
-        cpu = {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-               "sample": f"1 stream x {csize}^3, 2 update() after 1 warm-up ({sec:.2f} s/step), NumPy/pocketfft "
-                         "restatement of the reference's un-fused 7-FFT step"}
+        cpu = {"value": rate, "unit": "cell-updates/s", "cores": HOST_CORES, "kind": "port",
+               "sample": f"1 of the {n_total} streams x {csize}^3, 2 update() after 1 warm-up ({sec:.2f} s/step), "
+                         "NumPy/pocketfft restatement of the reference's un-fused 7-FFT step, "
+                         f"{o.get_workers()} worker threads"}
 
     if rank == 0:
         line = {"metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,

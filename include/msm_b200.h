@@ -122,6 +122,15 @@ int msm_upload_begin(msm_ctx* ctx, int32_t stream, const double* psi_interleaved
 int msm_download_begin(msm_ctx* ctx, int32_t stream, double* re, double* im);
 int msm_transfers_wait(msm_ctx* ctx);
 int msm_chunk_streams(const msm_ctx* ctx, int32_t* chunk);
+/* A ticket for every download enqueued so far; msm_download_wait blocks the CALLING thread (any thread -- the one
+ * exception to "one host thread per context": the dump writer threads of msm_sim_dump use it) until those downloads
+ * have landed in their host buffers, without touching the compute stream (the reference's dump is a synchronous
+ * `array.host()`, utils/io.rs:46-47). */
+int msm_download_ticket(msm_ctx* ctx, uint64_t* ticket);
+int msm_download_wait(msm_ctx* ctx, uint64_t ticket);
+/* Pinned host memory for asynchronous transfers (cudaMallocHost / cudaFreeHost). */
+int msm_host_alloc(msm_ctx* ctx, size_t bytes, void** out);
+int msm_host_free(msm_ctx* ctx, void* p);
 /* psi_k as the reference holds it after `update()` (second drift applied, :574). */
 int msm_get_psik_interleaved(msm_ctx* ctx, int32_t stream, double* out /* 2*n^dims */);
 
@@ -284,7 +293,15 @@ int msm_sim_get_psi(msm_sim* sim, int32_t stream, double* re, double* im);
 /* Write `sim-data/<sim_name>/psi_%05d_real|_imag` (two extension-less NPY v1 files, f64, shape (n,n|1,n|1,1)),
  * the layout of `complex_array_to_disk` (utils/io.rs:34-88, simulation_object.rs:1155-1158).  SURVEY row f-2. */
 int msm_sim_dump(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index);
-/* Join the background NPY writers (the reference joins its I/O threads when a stream finishes, :651-655). */
+/* The `output_potential` branch of dump() (simulation_object.rs:1167-1180): `calculate_potential()` of the stream, then
+ * `potential_%05d_real|_imag` in the same layout; phi is real, so the imaginary file is all zeros, as in the reference. */
+int msm_sim_dump_potential(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name,
+                           uint32_t dump_index);
+/* msm_sim_dump only ENQUEUES the inverse transform, plane split and device-to-host copy (pinned staging pool, copy
+ * stream) and hands the planes to writer threads; the step loop is not stalled (the reference blocks in `array.host()`,
+ * utils/io.rs:46-47).  A writer that fails (RuntimeError::IOError, utils/error.rs:5-27; the reference panics in
+ * `expect("write to disk failed")`) makes the next msm_sim_dump* or msm_sim_wait_io return MSM_E_IO.
+ * msm_sim_wait_io joins the background NPY writers (the reference joins its I/O threads when a stream finishes, :651-655). */
 int msm_sim_wait_io(msm_sim* sim);
 
 /* host scalars, exported for the parity tests of rows a7/a8/a16 */

@@ -86,6 +86,10 @@ PROTOTYPES = {
     "msm_download_begin": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_transfers_wait": (C.c_int, [_vp]),
     "msm_chunk_streams": (C.c_int, [_vp, _ip]),
+    "msm_download_ticket": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "msm_download_wait": (C.c_int, [_vp, C.c_uint64]),
+    "msm_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "msm_host_free": (C.c_int, [_vp, _vp]),
     "msm_get_psik_interleaved": (C.c_int, [_vp, C.c_int32, _dp]),
     "msm_potential_max": (C.c_int, [_vp, _ip, _dp]),
     "msm_get_potential": (C.c_int, [_vp, C.c_int32, _dp]),
@@ -120,6 +124,7 @@ PROTOTYPES = {
     "msm_sim_state": (C.c_int, [_vp, C.c_int32, C.POINTER(MsmStreamState)]),
     "msm_sim_get_psi": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_sim_dump": (C.c_int, [_vp, C.c_int32, C.c_char_p, C.c_char_p, C.c_uint32]),
+    "msm_sim_dump_potential": (C.c_int, [_vp, C.c_int32, C.c_char_p, C.c_char_p, C.c_uint32]),
     "msm_sim_wait_io": (C.c_int, [_vp]),
     "msm_get_tau": (C.c_double, [C.c_double] * 6 + [C.c_int32]),
     "msm_supercomoving_boxsize": (C.c_double, [C.c_double] * 5),

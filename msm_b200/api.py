@@ -420,6 +420,11 @@ class SimulationObject:
         """`complex_array_to_disk` layout: <root>/<sim_name>/psi_%05d_real|_imag (utils/io.rs:34-88)."""
         check(lib.msm_sim_dump(self.handle, stream, root_dir.encode(), sim_name.encode(), dump_index), self.handle, sim=True)
 
+    def dump_potential(self, stream: int, root_dir: str, sim_name: str, dump_index: int) -> None:
+        """`output_potential` (simulation_object.rs:1167-1180): <root>/<sim_name>/potential_%05d_real|_imag (imag = 0)."""
+        check(lib.msm_sim_dump_potential(self.handle, stream, root_dir.encode(), sim_name.encode(), dump_index),
+              self.handle, sim=True)
+
     def wait_io(self) -> None:
         check(lib.msm_sim_wait_io(self.handle), self.handle, sim=True)
 

@@ -18,7 +18,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -432,6 +434,11 @@ struct msm_ctx {
     cudaEvent_t dl_ready[2] = {nullptr, nullptr}, dl_copied[2] = {nullptr, nullptr};
     char dl_used[2] = {0, 0};
     int dl_next = 0;
+    // download tickets (msm_download_ticket / msm_download_wait): a ring of events on the copy stream; writer threads
+    // of the host-logic level wait on them, hence the mutex
+    std::mutex tk_mu;
+    cudaEvent_t tk_ev[64] = {};
+    uint64_t tk_next = 0;
     // profiling
     bool prof = false;
     std::vector<ProfEvent> prof_pending;
@@ -795,6 +802,14 @@ int dt_potential_tail(msm_ctx* ctx, const int* ids, int ns, unsigned long long* 
     return poisson(ctx, (ns + 1) / 2, true, maxbits, /*x_fwd_done=*/true, false);
 }
 
+// psi of stream s changes: its cached max|phi| is stale, and so is a value of it that still waits in `maxbits`
+// after a non-blocking msm_step (the slot keeps its position in the list, marked -1)
+void invalidate_stream(msm_ctx* ctx, int s) {
+    ctx->pmax_valid[s] = 0;
+    for (int& q : ctx->pmax_pending)
+        if (q == s) q = -1;
+}
+
 int fetch_pending_pmax(msm_ctx* ctx) {
     if (ctx->pmax_pending.empty()) return MSM_OK;
     const size_t n = ctx->pmax_pending.size();
@@ -803,10 +818,20 @@ int fetch_pending_pmax(msm_ctx* ctx) {
         return fail(ctx, MSM_E_CUDA, "fetching max|phi| failed");
     for (size_t i = 0; i < n; ++i) {
         const int s = ctx->pmax_pending[i];
+        if (s < 0) continue;   // invalidated since (invalidate_stream)
         ctx->pmax_cache[s] = ctx->h_scal[ctx->S + 2 + i];
         ctx->pmax_valid[s] = 1;
     }
     ctx->pmax_pending.clear();
+    return MSM_OK;
+}
+
+// RuntimeError::NanOrInf (utils/error.rs:10; the reference only checks in debug builds, utils/grid.rs:66-105): the max
+// reduction works on bit patterns, so a NaN / Inf anywhere in phi arrives here as a non-finite max|phi|
+int check_finite(msm_ctx* ctx, const std::vector<int>& ids, const double* v, const char* what) {
+    for (int s : ids)
+        if (!std::isfinite(v[s]))
+            return fail(ctx, MSM_E_NAN, std::string("NaN or Inf in ") + what + " of stream " + std::to_string(s));
     return MSM_OK;
 }
 
@@ -1038,6 +1063,8 @@ void msm_destroy(msm_ctx* ctx) {
         if (ctx->dl_ready[i]) cudaEventDestroy(ctx->dl_ready[i]);
         if (ctx->dl_copied[i]) cudaEventDestroy(ctx->dl_copied[i]);
     }
+    for (cudaEvent_t e : ctx->tk_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->tm_a) cudaEventDestroy(ctx->tm_a);
     if (ctx->tm_b) cudaEventDestroy(ctx->tm_b);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -1072,7 +1099,7 @@ int msm_set_psi(msm_ctx* ctx, int32_t s, const double* psi) {
     CU(cudaStreamSynchronize(ctx->st));
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     return MSM_OK;
 }
 
@@ -1089,7 +1116,7 @@ int msm_set_psi_planes(msm_ctx* ctx, int32_t s, const double* re, const double* 
     CU(cudaStreamSynchronize(ctx->st));
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     return MSM_OK;
 }
 
@@ -1230,7 +1257,7 @@ int msm_upload_begin(msm_ctx* ctx, int32_t s, const double* psi) {
     ctx->up_pending[s] = 1;
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     return MSM_OK;
 }
 
@@ -1272,6 +1299,49 @@ int msm_download_begin(msm_ctx* ctx, int32_t s, double* re, double* im) {
     if (im) CU(cudaMemcpyAsync(im, planes + ctx->C, pb, cudaMemcpyDeviceToHost, ctx->copy_st));
     CU(cudaEventRecord(ctx->dl_copied[b], ctx->copy_st));
     ctx->dl_used[b] = 1;
+    return MSM_OK;
+}
+
+int msm_download_ticket(msm_ctx* ctx, uint64_t* ticket) {
+    if (!ctx || !ticket) return fail(ctx, MSM_E_ARG, "msm_download_ticket: bad argument");
+    if (!ctx->copy_st) return fail(ctx, MSM_E_STATE, "msm_download_ticket: no download has been started");
+    CU(cudaSetDevice(ctx->cfg.device));
+    std::lock_guard<std::mutex> lock(ctx->tk_mu);
+    cudaEvent_t& e = ctx->tk_ev[ctx->tk_next % 64];
+    if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // (a waiter of ticket t - 64 whose event is re-recorded here waits for the newer record: later, never earlier)
+    CU(cudaEventRecord(e, ctx->copy_st));
+    *ticket = ctx->tk_next++;
+    return MSM_OK;
+}
+
+int msm_download_wait(msm_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return MSM_E_ARG;
+    cudaEvent_t e;
+    {
+        std::lock_guard<std::mutex> lock(ctx->tk_mu);
+        if (ticket >= ctx->tk_next) return MSM_E_ARG;
+        e = ctx->tk_ev[ticket % 64];
+    }
+    // no fail(): this runs on writer threads, ctx->err belongs to the thread that owns the context
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess || cudaEventSynchronize(e) != cudaSuccess) return MSM_E_CUDA;
+    return MSM_OK;
+}
+
+int msm_host_alloc(msm_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out || bytes == 0) return fail(ctx, MSM_E_ARG, "msm_host_alloc: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (cudaMallocHost(out, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(ctx, MSM_E_NOMEM, "msm_host_alloc: cudaMallocHost failed");
+    }
+    return MSM_OK;
+}
+
+int msm_host_free(msm_ctx* ctx, void* p) {
+    if (!ctx) return MSM_E_ARG;
+    if (p) cudaFreeHost(p);
     return MSM_OK;
 }
 
@@ -1318,11 +1388,7 @@ static int density_from_psik(msm_ctx* ctx, const int* ids, int ns, bool summed, 
     return run_transform(ctx, true, ids, ns, ctx->X, 1, ctx->Tscr, 0, o);
 }
 
-int msm_potential_max(msm_ctx* ctx, const int32_t* active, double* out) {
-    if (!ctx || !out) return fail(ctx, MSM_E_ARG, "msm_potential_max: bad argument");
-    CU(cudaSetDevice(ctx->cfg.device));
-    std::vector<int> ids = active_list(ctx, active);
-    if (ids.empty()) return MSM_OK;
+static int potential_max_of(msm_ctx* ctx, const std::vector<int>& ids, double* out) {
     int rc = fetch_pending_pmax(ctx);
     if (rc) return rc;
     {
@@ -1374,6 +1440,27 @@ int msm_potential_max(msm_ctx* ctx, const int32_t* active, double* out) {
         ctx->pmax_valid[ids[i]] = 1;
     }
     return MSM_OK;
+}
+
+int msm_potential_max(msm_ctx* ctx, const int32_t* active, double* out) {
+    if (!ctx || !out) return fail(ctx, MSM_E_ARG, "msm_potential_max: bad argument");
+    CU(cudaSetDevice(ctx->cfg.device));
+    std::vector<int> ids = active_list(ctx, active);
+    if (ids.empty()) return MSM_OK;
+    int rc = potential_max_of(ctx, ids, out);
+    if (rc) return rc;
+    // NaN / Inf guard.  Two independent streams share one complex pair buffer (rho_a + i rho_b), so a non-finite stream
+    // also poisons its partner's max|phi|: every suspect is solved again on its own before it is blamed.
+    std::vector<int> bad;
+    for (int s : ids)
+        if (!std::isfinite(out[s])) bad.push_back(s);
+    if (bad.size() > 1 && ctx->cfg.coupling == MSM_COUPLING_INDEPENDENT) {
+        for (int s : bad) {
+            ctx->pmax_valid[s] = 0;
+            if ((rc = potential_max_of(ctx, std::vector<int>{s}, out))) return rc;
+        }
+    }
+    return check_finite(ctx, ids, out, "the potential");
 }
 
 int msm_get_potential(msm_ctx* ctx, int32_t s, double* phi) {
@@ -1531,6 +1618,7 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
         if ((rc = fetch_pending_pmax(ctx))) return rc;   // same sync
         CU(cudaStreamSynchronize(ctx->st));
         for (int s : ids) alias_mass[s] = ctx->h_scal[s];
+        if ((rc = check_finite(ctx, ids, alias_mass, "psi_k (alias sum)"))) return rc;
     }
     return MSM_OK;
 }
@@ -1655,7 +1743,7 @@ int msm_ic_cold_gauss(msm_ctx* ctx, int32_t s, const double* mean, const double*
     if (rc) return rc;
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     return MSM_OK;
 }
 
@@ -1698,7 +1786,7 @@ int msm_ic_cold_gauss_kspace(msm_ctx* ctx, int32_t s, const double* mean, const 
     if (rc) return rc;
     ctx->in_k[s] = 0;   // what X holds now is the reference's spatial psi
     ctx->has_psi[s] = 1;
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     return MSM_OK;
 }
 
@@ -1715,7 +1803,7 @@ int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t s, double axis_length, double 
     if (rc) return rc;
     ctx->in_k[s] = 0;
     ctx->has_psi[s] = 1;
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     return MSM_OK;
 }
 
@@ -1730,7 +1818,7 @@ int msm_ic_copy(msm_ctx* ctx, int32_t dst, int32_t src) {
                            cudaMemcpyDeviceToDevice, ctx->st));
     ctx->in_k[dst] = ctx->in_k[src];
     ctx->has_psi[dst] = 1;
-    ctx->pmax_valid[dst] = 0;
+    invalidate_stream(ctx, dst);
     return MSM_OK;
 }
 
@@ -1743,7 +1831,7 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     CU(cudaSetDevice(ctx->cfg.device));
     if (scheme == MSM_SCHEME_POISSON) {   // ics.rs:495-558; statistically the reference's sampler (its rng is unseeded, :497)
         if (!(n_tot > 0.0)) return fail(ctx, MSM_E_ARG, "msm_sample_perturbation: n_tot must be positive");
-        ctx->pmax_valid[s] = 0;
+        invalidate_stream(ctx, s);
         if (int rc = wait_upload(ctx, s)) return rc;
         k_sample_poisson<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed,
                                                                 pow(ctx->cfg.dx, (double)ctx->dims), n_tot, ctx->n, ctx->lb);
@@ -1753,7 +1841,7 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t se
     }
     const double sqrt_dv = sqrt(pow(ctx->cfg.dx, (double)ctx->dims));
     const double div = sqrt(n_tot) * (scheme == MSM_SCHEME_WIGNER ? 2.0 : sqrt(2.0));   // ics.rs:581 / :625
-    ctx->pmax_valid[s] = 0;
+    invalidate_stream(ctx, s);
     if (int rc = wait_upload(ctx, s)) return rc;
     k_sample_gauss<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->X + (size_t)s * ctx->C, ctx->C, seed, sqrt_dv, div, ctx->n, ctx->lb);
     ctx->launches++;

@@ -284,9 +284,16 @@ __device__ __forceinline__ double warp_sum(double x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
 }
-__device__ __forceinline__ double warp_max(double x) {
+// max|.| is reduced on the BIT PATTERNS of |x| (non-negative doubles order like unsigned integers, and every NaN
+// pattern lies above +Inf): unlike fmax, which drops NaNs, a NaN or Inf anywhere in phi reaches the host, which turns
+// it into MSM_E_NAN (utils/grid.rs:66-105 check_complex_for_nans, utils/error.rs:10 RuntimeError::NanOrInf).
+__device__ __forceinline__ unsigned long long abs_bits(double x) {
+    return (unsigned long long)__double_as_longlong(fabs(x));
+}
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned long long warp_umax(unsigned long long x) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    for (int o = 16; o > 0; o >>= 1) x = umax64(x, __shfl_xor_sync(0xffffffffu, x, o));
     return x;
 }
 
@@ -450,7 +457,8 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
     double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>() + table_elems<N, LOP, SOP>());
-    __shared__ double red[2][32], red2[32];
+    __shared__ double red[2][32];
+    __shared__ unsigned long long redm[2][32];
     double2* tws = sm + exchange_elems<N, LOP, XL>();
     double* ks = reinterpret_cast<double*>(tws + (kTwSmem ? N : 0));
     double2* dts = tws + (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0);
@@ -463,7 +471,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
         for (int i = threadIdx.x; i < N; i += THREADS) ks[i] = p.ksq[i];
     }
     if constexpr (kTwSmem || sop_needs_k2(SOP)) __syncthreads();
-    double run_max = 0.0, run_max2 = 0.0;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
+    unsigned long long run_max = 0ull, run_max2 = 0ull;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
     int item_parity = 0;
 
     const int tid = threadIdx.x;
@@ -714,7 +722,8 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
 
         // ---- store (last-stage output order) ----
         fresh_offsets(v[0].x);
-        double acc = 0.0, acc2 = 0.0;
+        double acc = 0.0;
+        unsigned long long mx = 0ull, mx2 = 0ull;
 #pragma unroll
         for (int c = 0; c < NBL; ++c) {
 #pragma unroll
@@ -746,8 +755,8 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
                     x.y *= m;
                 }
                 if constexpr (SOP == S_MAX) {
-                    acc = fmax(acc, fabs(x.x));
-                    acc2 = fmax(acc2, fabs(x.y));
+                    mx = umax64(mx, abs_bits(x.x));
+                    mx2 = umax64(mx2, abs_bits(x.y));
                 }
                 if constexpr (sop_is_rho(SOP)) {
                     // rho = A real(psi conj(psi))   (simulation_object.rs:1051-1062)
@@ -820,15 +829,15 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             item_parity ^= 1;
         }
         if constexpr (SOP == S_MAX) {
-            run_max = fmax(run_max, acc);
-            run_max2 = fmax(run_max2, acc2);
+            run_max = umax64(run_max, mx);
+            run_max2 = umax64(run_max2, mx2);
             if (p.gsz > 1) {   // several buffers per CTA: flush per item (not used by the solver, kept for generality)
-                const double m1 = warp_max(run_max), m2 = warp_max(run_max2);
+                const unsigned long long m1 = warp_umax(run_max), m2 = warp_umax(run_max2);
                 if ((tid & 31) == 0) {
-                    if (m1 > 0.0) atomicMax(&p.maxbits[2 * li], (unsigned long long)__double_as_longlong(m1));
-                    if (m2 > 0.0) atomicMax(&p.maxbits[2 * li + 1], (unsigned long long)__double_as_longlong(m2));
+                    if (m1) atomicMax(&p.maxbits[2 * li], m1);
+                    if (m2) atomicMax(&p.maxbits[2 * li + 1], m2);
                 }
-                run_max = run_max2 = 0.0;
+                run_max = run_max2 = 0ull;
             }
         }
     }
@@ -845,20 +854,20 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     if constexpr (SOP == S_MAX) {
         if (p.gsz == 1 && g < p.ns) {
             // max|re|, max|im| of this CTA's tiles of buffer g; bit patterns of non-negative doubles order like integers
-            const double m1 = warp_max(run_max), m2 = warp_max(run_max2);
+            const unsigned long long m1 = warp_umax(run_max), m2 = warp_umax(run_max2);
             if ((tid & 31) == 0) {
-                red[0][tid >> 5] = m1;
-                red2[tid >> 5] = m2;
+                redm[0][tid >> 5] = m1;
+                redm[1][tid >> 5] = m2;
             }
             __syncthreads();
             if (tid == 0) {
-                double a = 0.0, b = 0.0;
+                unsigned long long a = 0ull, b = 0ull;
                 for (int w = 0; w < (THREADS + 31) / 32; ++w) {
-                    a = fmax(a, red[0][w]);
-                    b = fmax(b, red2[w]);
+                    a = umax64(a, redm[0][w]);
+                    b = umax64(b, redm[1][w]);
                 }
-                if (a > 0.0) atomicMax(&p.maxbits[2 * g], (unsigned long long)__double_as_longlong(a));
-                if (b > 0.0) atomicMax(&p.maxbits[2 * g + 1], (unsigned long long)__double_as_longlong(b));
+                if (a) atomicMax(&p.maxbits[2 * g], a);
+                if (b) atomicMax(&p.maxbits[2 * g + 1], b);
             }
         }
     }

@@ -187,8 +187,14 @@ int main(int argc, char** argv) {
         if (scheme_id != MSM_SCHEME_NONE) CHECK_CTX(msm_sample_perturbation(ctx, (int)i, scheme_id, (uint64_t)seeds[i], n_tot));
 
     if (verbose) printf("%d streams, %d^%d grid, %s box\n", S, p.size, p.dims, p.expanding ? "expanding" : "static");
+    const bool output_potential = num(kv, "output_potential", 0.0) != 0.0;                           // :1167-1180
+    auto dump = [&](int s, uint32_t index) -> int {
+        int rc_ = msm_sim_dump(sim, s, out.c_str(), names[s].c_str(), index);
+        if (rc_ == MSM_OK && output_potential) rc_ = msm_sim_dump_potential(sim, s, out.c_str(), names[s].c_str(), index);
+        return rc_;
+    };
     if (!test_only) {
-        for (int s = 0; s < S; ++s) CHECK_SIM(msm_sim_dump(sim, s, out.c_str(), names[s].c_str(), 0));   // main.rs:61
+        for (int s = 0; s < S; ++s) CHECK_SIM(dump(s, 0));                                               // main.rs:61
         long updates = 0;
         while (msm_sim_not_finished(sim) && (max_updates < 0 || updates < max_updates)) {               // main.rs:65
             rc = msm_sim_update(sim);
@@ -204,10 +210,10 @@ int main(int argc, char** argv) {
             for (int s = 0; s < S; ++s) {
                 msm_stream_state st;
                 msm_sim_state(sim, s, &st);
-                if (st.dumped) CHECK_SIM(msm_sim_dump(sim, s, out.c_str(), names[s].c_str(), st.current_dumps));   // :620-631
+                if (st.dumped) CHECK_SIM(dump(s, st.current_dumps));                                     // :620-631
             }
         }
-        msm_sim_wait_io(sim);
+        CHECK_SIM(msm_sim_wait_io(sim));                                                                 // RuntimeError::IOError
         if (verbose) {
             unsigned long long steps = 0;
             for (int s = 0; s < S; ++s) {

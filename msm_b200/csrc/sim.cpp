@@ -13,9 +13,15 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <errno.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -116,6 +122,17 @@ struct Stream {
 
 }  // namespace
 
+// dump staging (row f-2): a small pool of pinned host buffers, 2 * cells doubles each (re plane | im plane).  The D2H
+// copy of a dump runs on the library's copy stream while the step kernels continue; writer threads wait for their
+// copy (msm_download_wait), write the NPY files and hand the buffer back.
+struct DumpPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<double*> all, free_;
+    bool failed = false;          // a writer failed: reported by the next msm_sim_dump* / msm_sim_wait_io as MSM_E_IO
+    std::string error;
+};
+
 struct msm_sim {
     msm_sim_params p{};
     msm_derived d{};
@@ -123,6 +140,7 @@ struct msm_sim {
     msm_ctx* ctx = nullptr;
     std::vector<Stream> st;
     std::vector<std::thread> io;
+    DumpPool pool;
     std::string err;
 };
 
@@ -185,7 +203,15 @@ bool write_npy(const std::string& path, const double* data, int dims, int n) {
     ok = ok && fputc('\n', f) != EOF;
     size_t count = 1;
     for (int d = 0; d < dims; ++d) count *= (size_t)n;
-    ok = ok && fwrite(data, sizeof(double), count, f) == count;
+    if (data) {
+        ok = ok && fwrite(data, sizeof(double), count, f) == count;
+    } else {   // an all-zero plane (the imaginary file of a potential dump, simulation_object.rs:1167-1180)
+        std::vector<double> z(std::min<size_t>(count, 1 << 16), 0.0);
+        for (size_t done = 0; done < count && ok; done += z.size()) {
+            const size_t m = std::min(z.size(), count - done);
+            ok = fwrite(z.data(), sizeof(double), m, f) == m;
+        }
+    }
     ok = (fclose(f) == 0) && ok;
     return ok;
 }
@@ -214,12 +240,90 @@ std::vector<int> run_groups(int n, int chunk) {
     return bounds;
 }
 
-void mkdirs(const std::string& path) {
+bool mkdirs(const std::string& path) {
     std::string cur;
     for (size_t i = 0; i < path.size(); ++i) {
         cur.push_back(path[i]);
-        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0777);
+        if (path[i] == '/' || i + 1 == path.size())
+            if (mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST && !(cur == "/")) return false;
     }
+    struct stat sb;
+    return stat(path.c_str(), &sb) == 0 && S_ISDIR(sb.st_mode);
+}
+
+size_t sim_cells(const msm_sim* sim) {
+    size_t c = 1;
+    for (int d = 0; d < sim->p.dims; ++d) c *= (size_t)sim->p.size;
+    return c;
+}
+
+int pool_error(msm_sim* sim) {
+    std::lock_guard<std::mutex> lock(sim->pool.mu);
+    if (!sim->pool.failed) return MSM_OK;
+    sim->err = sim->pool.error;
+    return MSM_E_IO;
+}
+
+// a free staging buffer; grows the pool up to MSM_B200_DUMP_BUFFERS (default 4), then waits for a writer to finish
+int pool_acquire(msm_sim* sim, double** out) {
+    DumpPool& P = sim->pool;
+    size_t cap = 4;
+    if (const char* e = getenv("MSM_B200_DUMP_BUFFERS")) cap = (size_t)std::max(1, atoi(e));
+    std::unique_lock<std::mutex> lock(P.mu);
+    for (;;) {
+        if (!P.free_.empty()) {
+            *out = P.free_.back();
+            P.free_.pop_back();
+            return MSM_OK;
+        }
+        if (P.all.size() < cap) {
+            void* p = nullptr;
+            lock.unlock();
+            const int rc = msm_host_alloc(sim->ctx, 2 * sizeof(double) * sim_cells(sim), &p);
+            lock.lock();
+            if (rc == MSM_OK) {
+                P.all.push_back((double*)p);
+                *out = (double*)p;
+                return MSM_OK;
+            }
+            if (P.all.empty()) {
+                sim->err = msm_last_error(sim->ctx);
+                return rc;
+            }
+            // no more pinned memory: live with the buffers we have
+        }
+        P.cv.wait(lock);
+    }
+}
+
+void pool_release(msm_sim* sim, double* buf) {
+    {
+        std::lock_guard<std::mutex> lock(sim->pool.mu);
+        sim->pool.free_.push_back(buf);
+    }
+    sim->pool.cv.notify_all();
+}
+
+void pool_fail(msm_sim* sim, const std::string& what) {
+    std::lock_guard<std::mutex> lock(sim->pool.mu);
+    if (!sim->pool.failed) sim->pool.error = what;
+    sim->pool.failed = true;
+}
+
+// two writer threads per dump, one per plane (utils/io.rs:58-60,72-74); the last one returns the staging buffer
+void spawn_writers(msm_sim* sim, double* buf, bool has_ticket, uint64_t ticket, const std::string& path_re,
+                   const std::string& path_im, bool imag_zero) {
+    const int dims = sim->p.dims, n = sim->p.size;
+    const size_t cells = sim_cells(sim);
+    auto left = std::make_shared<std::atomic<int>>(2);
+    auto job = [=](const std::string& path, const double* data) {
+        bool ok = !has_ticket || msm_download_wait(sim->ctx, ticket) == MSM_OK;
+        if (!ok) pool_fail(sim, "dump: the device-to-host copy failed for " + path);
+        else if (!write_npy(path, data, dims, n)) pool_fail(sim, "dump: cannot write " + path + ": " + strerror(errno));
+        if (left->fetch_sub(1) == 1) pool_release(sim, buf);
+    };
+    sim->io.emplace_back(job, path_re, (const double*)buf);
+    sim->io.emplace_back(job, path_im, imag_zero ? (const double*)nullptr : (const double*)(buf + cells));
 }
 
 }  // namespace
@@ -336,12 +440,18 @@ int msm_sim_wait_io(msm_sim* sim) {
     for (auto& t : sim->io)
         if (t.joinable()) t.join();
     sim->io.clear();
-    return MSM_OK;
+    const int rc = pool_error(sim);   // RuntimeError::IOError (utils/error.rs:5-27); the reference panics in the writer
+    if (rc) {
+        std::lock_guard<std::mutex> lock(sim->pool.mu);
+        sim->pool.failed = false;     // reported once
+    }
+    return rc;
 }
 
 void msm_sim_destroy(msm_sim* sim) {
     if (!sim) return;
     msm_sim_wait_io(sim);
+    for (double* b : sim->pool.all) msm_host_free(sim->ctx, b);
     msm_destroy(sim->ctx);
     delete sim;
 }
@@ -358,13 +468,15 @@ int msm_sim_set_psi(msm_sim* sim, int32_t stream, const double* psi) {
     if (!sim) return MSM_E_ARG;
     int rc = msm_set_psi(sim->ctx, stream, psi);
     if (rc) sim->err = msm_last_error(sim->ctx);
+    else sim->st[stream].aliased = 0;   // a new wavefunction
     return rc;
 }
 
 int msm_sim_not_finished(const msm_sim* sim) {
     if (!sim) return 0;
+    // a stream that crossed alias_threshold has stopped for good (the reference panics there, :607-617)
     for (const auto& st : sim->st)
-        if (not_finished(sim, st)) return 1;
+        if (not_finished(sim, st) && !st.aliased) return 1;
     return 0;
 }
 
@@ -374,12 +486,14 @@ static int update_streams(msm_sim* sim, const int32_t* subset) {
     const int S = p.n_streams;
     const bool summed = p.coupling == MSM_COUPLING_SUMMED;
     std::vector<int32_t> active(S, 0);
-    int nact = 0;
+    int nact = 0, head = -1;
     for (int s = 0; s < S; ++s) {
         if (subset && !subset[s]) continue;
         sim->st[s].dumped = 0;
-        if (not_finished(sim, sim->st[s])) {
+        // a stream that crossed alias_threshold stops there: the reference panics (:607-617)
+        if (not_finished(sim, sim->st[s]) && !sim->st[s].aliased) {
             active[s] = 1;
+            if (head < 0) head = s;
             ++nact;
         }
     }
@@ -393,17 +507,19 @@ static int update_streams(msm_sim* sim, const int32_t* subset) {
         sim->err = msm_last_error(sim->ctx);
         return rc;
     }
+    // The host scalars of the step are staged in copies and committed only after msm_step succeeded, so that a failed
+    // step leaves time / tau / a(t) consistent with psi on the device.
+    std::vector<Stream> next(sim->st);
     for (int s = 0; s < S; ++s) {
         if (!active[s]) continue;
-        Stream& st = sim->st[s];
+        Stream& st = next[s];
         bool dmp = false;
         double dt = 0.0;
-        get_timestep(sim, st, pmax[s], &dmp, &dt);                               // :500 / :695
-        if (summed && s > 0) {   // shared potential => identical scalars; keep the streams in lock step
-            int h = 0;
-            while (!active[h]) ++h;
-            dmp = dump[h];
-            dt = dts[h];
+        if (summed && s != head) {   // shared potential => identical scalars; keep the streams in lock step
+            dmp = dump[head];
+            dt = dts[head];
+        } else {
+            get_timestep(sim, st, pmax[s], &dmp, &dt);                           // :500 / :695
         }
         dump[s] = dmp;
         dts[s] = dt;
@@ -435,6 +551,7 @@ static int update_streams(msm_sim* sim, const int32_t* subset) {
     for (int s = 0; s < S; ++s) {
         if (!active[s]) continue;
         Stream& st = sim->st[s];
+        st = next[s];
         if (!p.expanding) st.time = st.time + dts[s];                            // :590
         st.alias_mass = alias[s];
         st.aliased = alias[s] > p.alias_threshold ? 1 : 0;                       // :1288
@@ -606,30 +723,48 @@ int msm_sim_get_psi(msm_sim* sim, int32_t stream, double* re, double* im) {
     return rc;
 }
 
-int msm_sim_dump(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index) {
-    if (!sim || !root_dir || !sim_name) return MSM_E_ARG;
-    const int dims = sim->p.dims, n = sim->p.size;
-    size_t count = 1;
-    for (int d = 0; d < dims; ++d) count *= (size_t)n;
+// `dump()` (simulation_object.rs:1113-1223) without stalling the step loop: the call only ENQUEUES the inverse transform
+// + plane split on the compute stream and the D2H copy on the copy stream (msm_download_begin) into a pinned staging
+// buffer; two writer threads wait for that copy and write the NPY files.  The reference's `array.host()` blocks
+// (utils/io.rs:46-47).  A failed writer surfaces as MSM_E_IO from the next msm_sim_dump* or msm_sim_wait_io.
+static int dump_field(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index,
+                      bool potential) {
+    if (!sim || !root_dir || !sim_name || stream < 0 || stream >= sim->p.n_streams)
+        return sfail(sim, MSM_E_ARG, "msm_sim_dump: bad argument");
+    if (int rc = pool_error(sim)) return rc;
     // at most 2 * MAX_CONCURRENT_GRID_WRITES live writers (simulation_object.rs:39,:1123)
-    if (sim->io.size() >= 32) msm_sim_wait_io(sim);
-    std::vector<double>* re = new std::vector<double>(count);
-    std::vector<double>* im = new std::vector<double>(count);
-    int rc = msm_get_psi(sim->ctx, stream, re->data(), im->data());
+    if (sim->io.size() >= 32)
+        if (int rc = msm_sim_wait_io(sim)) return rc;
+    const std::string dir = std::string(root_dir) + "/" + sim_name;
+    if (!mkdirs(dir)) return sfail(sim, MSM_E_IO, "dump: cannot create directory " + dir + ": " + strerror(errno));   // :1119
+    double* buf = nullptr;
+    if (int rc = pool_acquire(sim, &buf)) return rc;
+    const size_t cells = sim_cells(sim);
+    uint64_t ticket = 0;
+    int rc;
+    if (potential) {   // calculate_potential + dump of phi (:1167-1180); rare, computed synchronously
+        rc = msm_get_potential(sim->ctx, stream, buf);
+    } else {
+        rc = msm_download_begin(sim->ctx, stream, buf, buf + cells);
+        if (!rc) rc = msm_download_ticket(sim->ctx, &ticket);
+    }
     if (rc) {
         sim->err = msm_last_error(sim->ctx);
-        delete re;
-        delete im;
+        pool_release(sim, buf);
         return rc;
     }
-    const std::string dir = std::string(root_dir) + "/" + sim_name;
-    mkdirs(dir);                                                                 // :1119
     char base[64];
-    snprintf(base, sizeof base, "/psi_%05u", dump_index);                        // :1155-1158
-    const std::string pr = dir + base + "_real", pi = dir + base + "_imag";      // io.rs:54-55
-    sim->io.emplace_back([=]() { write_npy(pr, re->data(), dims, n); delete re; });
-    sim->io.emplace_back([=]() { write_npy(pi, im->data(), dims, n); delete im; });
+    snprintf(base, sizeof base, "/%s_%05u", potential ? "potential" : "psi", dump_index);   // :1155-1158, :1171-1174
+    spawn_writers(sim, buf, !potential, ticket, dir + base + "_real", dir + base + "_imag", potential);   // io.rs:54-55
     return MSM_OK;
+}
+
+int msm_sim_dump(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index) {
+    return dump_field(sim, stream, root_dir, sim_name, dump_index, false);
+}
+
+int msm_sim_dump_potential(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index) {
+    return dump_field(sim, stream, root_dir, sim_name, dump_index, true);
 }
 
 }  // extern "C"

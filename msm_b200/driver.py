@@ -60,9 +60,14 @@ def run(cfg: RunConfig, out_root: str = "sim-data", rank: int = 0, nranks: int =
     sim = SimulationObject(cfg.parameters, n_streams=len(local), coupling=COUPLING_INDEPENDENT, device=device)
     load_initial_conditions(sim, cfg, local, base_dir)
     t0 = time.time()
+    def dump(li, s, index):                                          # simulation_object.rs:1113-1180
+        sim.dump(li, out_root, cfg.streams[s].sim_name, index)
+        if cfg.output_potential:                                     # :1167-1180
+            sim.dump_potential(li, out_root, cfg.streams[s].sim_name, index)
+
     if write:
         for li, s in enumerate(local):                               # main.rs:61 dump the initial condition
-            sim.dump(li, out_root, cfg.streams[s].sim_name, 0)
+            dump(li, s, 0)
     updates = 0
     while sim.not_finished() and (max_updates is None or updates < max_updates):   # main.rs:65-69
         sim.update()
@@ -70,7 +75,7 @@ def run(cfg: RunConfig, out_root: str = "sim-data", rank: int = 0, nranks: int =
         for li, s in enumerate(local):
             st = sim.state(li)
             if st.dumped and write:
-                sim.dump(li, out_root, cfg.streams[s].sim_name, st.current_dumps)
+                dump(li, s, st.current_dumps)
     sim.wait_io()
     steps = sum(int(sim.state(li).n_steps) for li in range(len(local)))
     wall = time.time() - t0
@@ -107,6 +112,8 @@ def export_params(cfg: RunConfig, path: str, base_dir: str = ".") -> None:
         lines.append(f"ics = File {raw}")
     else:
         raise NotImplementedError(ics["type"])
+    if cfg.output_potential:
+        lines.append("output_potential = 1")
     seeds = [s.seed for s in cfg.streams if s.seed is not None]
     if seeds:
         lines.append("seeds = " + ",".join(str(s) for s in seeds))

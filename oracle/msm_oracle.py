@@ -437,17 +437,18 @@ def _u53(hi, lo):
         * (1.0 / 9007199254740992.0)
 
 
-def philox_uniform(n_cells: int, seed: int, draw: int = 0) -> Tuple[np.ndarray, np.ndarray]:
-    """Two uniforms per cell: counter = (cell_lo, cell_hi, draw, 0), key = (seed_lo, seed_hi)."""
-    q = np.arange(n_cells, dtype=np.uint64)
+def philox_uniform(n_cells: int, seed: int, draw: int = 0, start: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Two uniforms per cell: counter = (cell_lo, cell_hi, draw, 0), key = (seed_lo, seed_hi); cells start .. start +
+    n_cells - 1 (the stream is counter-based, so a grid can be generated slab by slab)."""
+    q = np.arange(start, start + n_cells, dtype=np.uint64)
     x0, x1, x2, x3 = philox4x32_10(q & _M32, q >> np.uint64(32), np.full(n_cells, draw, np.uint64),
                                    np.zeros(n_cells, np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     return _u53(x0, x1), _u53(x2, x3)
 
 
-def philox_normal_pair(n_cells: int, seed: int, draw: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+def philox_normal_pair(n_cells: int, seed: int, draw: int = 0, start: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Box-Muller on `philox_uniform`: two independent N(0,1) per cell."""
-    u1, u2 = philox_uniform(n_cells, seed, draw)
+    u1, u2 = philox_uniform(n_cells, seed, draw, start)
     r = np.sqrt(-2.0 * np.log(u1))
     ang = 2.0 * math.pi * u2
     return r * np.cos(ang), r * np.sin(ang)
@@ -542,8 +543,15 @@ def sample_quantum_perturbation(psi: np.ndarray, p: SimulationParameters, sampli
         mag = np.sqrt(a / n)                                                    # :523
         out = mag * np.exp(1j * np.angle(psi))                                  # :535-544
         return out / sqrt_dv                                                    # :547-557
-    z0, z1 = philox_normal_pair(psi.size, seed, draw=0)
-    samples = (z0 + 1j * z1).reshape(psi.shape)                                 # :563-575 / :607-619
+    if psi.size >= _PAR_MIN and _WORKERS > 1:     # slab by slab on the worker threads: the same numbers, less memory
+        def slab(a):
+            lo = int(a[0].reshape(-1)[0])
+            z0, z1 = philox_normal_pair(a.size, seed, draw=0, start=lo)
+            return (z0 + 1j * z1).reshape(a.shape)
+        samples = _pmap(slab, np.arange(psi.size, dtype=np.int64).reshape(psi.shape))
+    else:
+        z0, z1 = philox_normal_pair(psi.size, seed, draw=0)
+        samples = (z0 + 1j * z1).reshape(psi.shape)                             # :563-575 / :607-619
     if scheme == "Wigner":
         samples = samples / (sqrt_n * 2.0)                                      # :578-585
     elif scheme == "Husimi":

@@ -1,4 +1,4 @@
-"""Coupled (summed-density) mode across ranks: torchrun --nproc-per-node R scripts/summed_multi_gpu.py
+"""Coupled (summed-density) mode across ranks: torchrun --nproc-per-node R tests/summed_multi_gpu_worker.py (launched by tests/test_gpu_multi.py)
 Each rank owns S/R streams; the density is ncclAllReduce'd inside libmsm_b200 (communicator from a unique id that
 rank 0 creates and torch.distributed broadcasts); every rank checks its streams against the CPU oracle ensemble."""
 import ctypes as C
