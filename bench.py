@@ -52,8 +52,9 @@ ALG_BYTES_PER_CELL_UPDATE = 480.0       # SURVEY 8d / DESIGN.md section 3: 3-pas
 
 
 def alg_bytes(coupling, s_local):
-    """algorithmic HBM bytes per cell-update of the 3-pass model: 480 independent, 296 + 368/S_local summed"""
-    return 480.0 if coupling == "independent" else 296.0 + 368.0 / s_local
+    """algorithmic HBM bytes per cell-update of the 3-pass model (SURVEY section 8d): 480 independent streams;
+    272 + 216 / S_local with the summed density (one real-field solve per potential for all local streams)"""
+    return 480.0 if coupling == "independent" else 272.0 + 216.0 / s_local
 
 
 def parse():
@@ -67,6 +68,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-summed", action="store_true", help="skip the summed-density (coupled) sub-record")
     ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU baseline sample (0 = auto)")
     ap.add_argument("--coupling", default="independent", choices=["independent", "summed"],
                     help="independent = the reference's semantics (headline); summed = north-star variant with one "
@@ -283,9 +285,9 @@ def main():
 
     coupling = m.COUPLING_SUMMED if args.coupling == "summed" else m.COUPLING_INDEPENDENT
 
-    def comm_kwargs():
+    def comm_kwargs(cpl=None):
         """a fresh ncclUniqueId per context (rank 0 creates, torch.distributed broadcasts); summed mode only"""
-        if coupling != m.COUPLING_SUMMED or world == 1:
+        if (coupling if cpl is None else cpl) != m.COUPLING_SUMMED or world == 1:
             return {}
         import ctypes as C
         from msm_b200._lib import lib
@@ -298,44 +300,51 @@ def main():
         return dict(rank=rank, nranks=world, n_streams_global=n_total, nccl_unique_id=bytes(uid.cpu().numpy().tobytes()))
 
     # ---- resident run: streams generated on the device, timed with CUDA events on the library's stream ----------
-    sim = None
-    note = ""
-    for chunk in (args.chunk, 4, 2):
-        try:
-            sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=coupling,
-                                     **comm_kwargs())
-            break
-        except m.MsmError as e:
-            if e.code != -7:
-                raise
-            note = f"chunk {chunk} did not fit"
-    if sim is None:
-        raise SystemExit("streams do not fit in device memory: " + note)
+    def resident(coupling_name):
+        cpl = m.COUPLING_SUMMED if coupling_name == "summed" else m.COUPLING_INDEPENDENT
+        sim, note, chunk = None, "", None
+        for chunk in (args.chunk, 4, 2):
+            try:
+                sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=cpl,
+                                         **comm_kwargs(cpl))
+                break
+            except m.MsmError as e:
+                if e.code != -7:
+                    raise
+                note = f"chunk {chunk} did not fit"
+        if sim is None:
+            raise SystemExit("streams do not fit in device memory: " + note)
+        g = sim.grid
+        build_streams(sim, n_local, rank * n_local, size)
+        for _ in range(args.warmup):
+            sim.update()
+        g.synchronize()
+        launches0 = g.launch_count()
+        g.profile_enable(True)
+        clocks = ClockSampler(device)
+        clocks.start()
+        barrier()
+        g.timer_start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.update()
+        ms = g.timer_stop()
+        wall = time.perf_counter() - t0
+        barrier()
+        clk = clocks.stop()
+        launches = g.launch_count() - launches0
+        prof = g.profile_read()
+        g.profile_enable(False)
+        ms = max_over_ranks(ms)
+        st = sim.state(0)
+        assert st.n_steps == args.warmup + args.steps and not st.aliased
+        return dict(sim=sim, ms=ms, wall=wall, clk=clk, launches=launches, prof=prof, chunk=chunk,
+                    value=cells * n_total * args.steps / (ms * 1e-3))
+
+    head = resident(args.coupling)
+    sim, g, ms, wall, clk, launches, prof, chunk, value = (head[k] for k in ("sim", "sim", "ms", "wall", "clk", "launches",
+                                                                             "prof", "chunk", "value"))
     g = sim.grid
-    build_streams(sim, n_local, rank * n_local, size)
-    for _ in range(args.warmup):
-        sim.update()
-    g.synchronize()
-    launches0 = g.launch_count()
-    g.profile_enable(True)
-    clocks = ClockSampler(device)
-    clocks.start()
-    barrier()
-    g.timer_start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sim.update()
-    ms = g.timer_stop()
-    wall = time.perf_counter() - t0
-    barrier()
-    clk = clocks.stop()
-    launches = g.launch_count() - launches0
-    prof = g.profile_read()
-    g.profile_enable(False)
-    ms = max_over_ranks(ms)
-    value = cells * n_total * args.steps / (ms * 1e-3)
-    st = sim.state(0)
-    assert st.n_steps == args.warmup + args.steps and not st.aliased
 
     # ---- roofline of the dominant kernel (CUDA events around every launch, same timed region) ------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -376,7 +385,32 @@ def main():
         out_im = torch.empty(cells, dtype=torch.float64, pin_memory=True)
         hnp, renp, imnp = host.numpy(), out_re.numpy(), out_im.numpy()
         hnp[:] = g.get_psi(0).reshape(-1).view(np.float64)        # a realistic wavefunction as the host-side IC
-        sim.close()
+    sim.close()
+
+    # ---- the north-star's coupled mode beside the headline: |psi|^2 summed over ALL streams (local accumulate ->
+    #      ncclAllReduce of the real density over NVLink -> replicated real-field Poisson solve), same streams, same steps
+    summed = None
+    if args.coupling == "independent" and not args.no_summed:
+        r = resident("summed")
+        r["sim"].close()
+        sp = r["prof"]
+        per = lambda pred: sum(x["ms_total"] for x in sp if pred(x["name"])) / args.steps       # noqa: E731
+        sb = alg_bytes("summed", n_local)
+        summed = {"value": r["value"], "unit": "cell-updates/s", "ms_per_step": r["ms"] / args.steps, "steps": args.steps,
+                  "allreduce_ms_per_step": per(lambda nm: nm.startswith("nccl_")),
+                  "poisson_ms_per_step": per(lambda nm: ",half>" in nm or ",nyquist>" in nm or "poisson" in nm
+                                             or nm.startswith(("pack_", "unpack_"))),
+                  "algorithmic_bytes_per_cell_update": sb,
+                  "step_frac": r["value"] / world * sb / 1e9 / (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+                                                              if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0),
+                  "gpu_launches": int(r["launches"]), "clocks": r["clk"],
+                  "what": "rho = (A/S) sum over all streams of |psi_s|^2: accumulated over the local streams inside the "
+                          "last inverse pass (real plane, 8 B/cell), ncclAllReduce of n^3 doubles in place, replicated "
+                          "real-field (R2C/C2R half-spectrum) Poisson solve; twice per step (kick potential, dt potential)",
+                  "kernels": [{"name": x["name"], "launches": x["launches"], "ms": round(x["ms_total"], 3),
+                               "GBps": round(x["algorithmic_bytes"] / (x["ms_total"] * 1e-3) / 1e9, 1)}
+                              for x in sorted(sp, key=lambda x: -x["ms_total"])]}
+    if not args.no_e2e:
         sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=coupling,
                                  **comm_kwargs())
         g = sim.grid
@@ -397,9 +431,10 @@ def main():
         sec = time.perf_counter() - t0
         barrier()
         sec = max_over_ranks(sec)
-        tab = 16 * size * n_local
+        # per update: drift coefficient + stream id per stream read by the device from mapped host memory (the drift
+        # tables themselves are built on the device), alias mass + max|phi| per stream written back the same way
         e2e = {"value": cells * n_total * args.steps / sec, "unit": "cell-updates/s",
-               "h2d_bytes_per_step": int(16 * cells * n_local / args.steps + tab + 16 * n_local),
+               "h2d_bytes_per_step": int(16 * cells * n_local / args.steps + 12 * n_local),
                "d2h_bytes_per_step": int(16 * cells * n_local / args.steps + 16 * n_local),
                "seconds": sec, "what": "msm_sim_run_streams (upload of every stream's IC from pinned host memory, K x "
                "update() per stream, download of every stream's final psi as re/im planes) inside the timed region; "
@@ -428,7 +463,8 @@ def main():
                            "l2": "inputs larger than L2 (2 GiB per stream vs 126 MB)",
                            "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall,
                            "cpu_affinity": numa},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "summed": summed}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -150,6 +150,30 @@ __global__ void k_unpack_real(const double* __restrict__ in, double2* __restrict
         out[q] = make_double2(in[q], 0.0);
 }
 
+// Per-step scalars reach the host through MAPPED pinned memory written by a kernel, not through cudaMemcpy: a small
+// D2H copy queues on the copy engine behind any bulk download in flight (a dump: 2 GiB at 512^3) and stalled the step
+// loop for the length of that transfer.
+__global__ void k_publish(const double* __restrict__ src, double* __restrict__ host_dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) host_dst[i] = src[i];
+}
+// per-axis drift factors dtab[s][m] = n^(-1/2) exp(-i c_s (2 pi k_m)^2) built on the device from the coefficients the
+// host left in mapped pinned memory: no H2D copy behind the bulk uploads of other streams
+// (simulation_object.rs:504-514 builds the full n^3 `k_evolution` array instead)
+__global__ void k_build_dtab(const double* __restrict__ host_coef, const int* __restrict__ host_ids, const double* __restrict__ ksq,
+                             double2* __restrict__ dtab, int n, double four_pi2, double sc) {
+    const int s = host_ids[blockIdx.x];
+    const double c = host_coef[s];
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        double sn, cs;
+        sincos(-c * (ksq[m] * four_pi2), &sn, &cs);
+        dtab[(long long)s * n + m] = make_double2(sc * cs, sc * sn);
+    }
+}
+__global__ void k_extract_real(const double* __restrict__ in, double* __restrict__ out, long long cells, int n, int lb) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x)
+        out[i] = in[blk_index(i, n, lb)];
+}
+
 // alias_out[s] = dv * sum_tiles partial[s][tile]    (fixed summation order: deterministic)
 __global__ void k_alias_reduce(const double* __restrict__ partial, double* __restrict__ out, int ntiles, int pitch,
                                double dv) {
@@ -397,12 +421,13 @@ struct msm_ctx {
     long long C = 0;
     cudaStream_t st = nullptr;
     double2 *X = nullptr, *Tscr = nullptr, *P = nullptr, *tw = nullptr, *dtab = nullptr;
-    double2* h_dtab = nullptr;   // pinned
+    double* h_coef = nullptr;    // pinned + mapped: drift coefficient per stream, read by k_build_dtab
+    int* h_ids = nullptr;        // pinned + mapped: streams whose tables are rebuilt
     cudaEvent_t dtab_done = nullptr;
     double* ksq = nullptr;
     double* alias_partial = nullptr;
     double* alias_out = nullptr;
-    double* h_scal = nullptr;    // pinned, 2*S doubles
+    double* h_scal = nullptr;    // pinned + mapped, 2*(S+2) doubles: written by k_publish, read by the host after a sync
     unsigned long long* maxbits = nullptr;
     double* scratch_small = nullptr;  // 4096 doubles
     double2 *ens_psi = nullptr, *ens_psik = nullptr;   // ensemble sums (row f-3), allocated on first use
@@ -447,6 +472,13 @@ struct msm_ctx {
     std::vector<msm_profile_record> prof_rec;
     std::string err;
     pass_launcher_t launcher = nullptr;
+    // real-field Poisson solve of the summed-density mode (dims == 3, n >= 16): the real plane of n^3 doubles IS a grid
+    // of n/2 x n x n complex pairs (x[2j], x[2j+1]); R2C / C2R run as n/2-point passes over it, the y / z passes as
+    // n-point passes over the half spectrum, and X[n/2] of every x line lives in a small Nyquist plane (n x n complex)
+    bool real_solve = false;
+    pass_launcher_t launcher_half = nullptr;
+    double2 *tw_half = nullptr, *wreal = nullptr, *nyq = nullptr;
+    int TXH = 0;           // contiguous-axis tile height of the n/2-point kernels
     bool xl = true;   // contiguous-axis thread mapping (MSM_B200_XL=0 selects the generic mapping, for A/B timing)
     bool fuse = true;  // fused passes (MSM_B200_FUSE=0 runs the plain 3+3 pass sequences, for A/B timing)
     int l2_prefetch = 1;   // MSM_B200_PREFETCH=0 switches the L2 prefetch of the next item off (A/B timing)
@@ -472,48 +504,65 @@ struct Geom {
     int axis, tiles_inner, ntiles, lvalid, olb = 0, alb = 0;
     long long outer, inner, lstride, astride, outer_lo = 0, astride_lo = 0;
 };
-Geom make_geom(const msm_ctx* c, int axis, int T) {
+// A grid as the pass kernels see it: `dims` axes of n points, except that the fastest one has nx (= n for the
+// wavefunctions, n / 2 for the half-spectrum grid of the real-field solve); slow axis blocked by 2^lb (blk_index).
+struct GridShape {
+    int dims, n, nx, lb;
+    long long cells() const {
+        long long c = nx;
+        for (int d = 1; d < dims; ++d) c *= n;
+        return c;
+    }
+};
+GridShape main_shape(const msm_ctx* c) { return GridShape{c->dims, c->n, c->n, c->lb}; }
+// what a pass runs on: the wavefunction grid, or one of the three views of the real-field solve
+enum Target { TG_MAIN = 0, TG_HALF_X = 1, TG_HALF_YZ = 2, TG_NYQ = 3 };
+
+Geom make_geom(const GridShape& s, int axis, int T) {
     Geom g{};
-    const int n = c->n;
+    const int n = s.n, nx = s.nx;
     g.axis = axis;
     if (axis == 0) {
-        const long long nlines = c->C / n;
+        const long long nlines = s.cells() / nx;
         g.ntiles = (int)((nlines + T - 1) / T);
         g.tiles_inner = g.ntiles;
-        g.inner = (long long)T * n;
+        g.inner = (long long)T * nx;
         g.outer = 0;
-        g.lstride = n;
+        g.lstride = nx;
         g.astride = 1;
         g.lvalid = (int)std::min<long long>(T, nlines);
     } else if (axis == 1) {
-        // along j for fixed (i, k0..k0+T-1): tile = i * (n/T) + m
-        const long long LO = 1LL << c->lb;
-        g.tiles_inner = n / T;
-        g.ntiles = g.tiles_inner * (c->dims == 3 ? n : 1);
+        // along j for fixed (i, k0..k0+T-1): tile = i * (nx/T) + m
+        const long long LO = 1LL << s.lb;
+        g.tiles_inner = nx / T;
+        g.ntiles = g.tiles_inner * (s.dims == 3 ? n : 1);
         g.inner = T;
-        g.olb = c->lb;                       // i = (i_hi, i_lo)
-        g.outer = (long long)n * n * LO;     // i_hi
-        g.outer_lo = n;                      // i_lo
+        g.olb = s.lb;                        // i = (i_hi, i_lo)
+        g.outer = (long long)nx * n * LO;    // i_hi
+        g.outer_lo = nx;                     // i_lo
         g.lstride = 1;
-        g.astride = (long long)n * LO;       // j
+        g.astride = (long long)nx * LO;      // j
         g.lvalid = T;
     } else {
-        // along i for fixed (j, k0..k0+T-1): tile = j * (n/T) + m
-        const long long LO = 1LL << c->lb;
-        g.tiles_inner = n / T;
-        g.ntiles = (int)(((long long)n * n) / T);
+        // along i for fixed (j, k0..k0+T-1): tile = j * (nx/T) + m
+        const long long LO = 1LL << s.lb;
+        g.tiles_inner = nx / T;
+        g.ntiles = (int)(((long long)nx * n) / T);
         g.inner = T;
-        g.outer = (long long)n * LO;         // j
+        g.outer = (long long)nx * LO;        // j
         g.lstride = 1;
-        g.alb = c->lb;
-        g.astride = (long long)n * n * LO;   // i_hi
-        g.astride_lo = n;                    // i_lo
+        g.alb = s.lb;
+        g.astride = (long long)nx * n * LO;  // i_hi
+        g.astride_lo = nx;                   // i_lo
         g.lvalid = T;
     }
     return g;
 }
+Geom make_geom(const msm_ctx* c, int axis, int T) { return make_geom(main_shape(c), axis, T); }
 
-const char* lop_name(int l) { return l == L_NONE ? "none" : l == L_DRIFT ? "drift" : l == L_KICK ? "kick" : "invx+kick"; }
+const char* lop_name(int l) {
+    return l == L_NONE ? "none" : l == L_DRIFT ? "drift" : l == L_KICK ? "kick" : l == L_C2R ? "c2r" : "invx+kick";
+}
 const char* sop_name(int s) {
     switch (s) {
         case S_NONE: return "none";
@@ -528,17 +577,20 @@ const char* sop_name(int s) {
         case S_RHO_KEEP_FX: return "psi+rho+fwdx";
         case S_RHO_ONLY_FX: return "rho+fwdx";
         case S_DRIFT_ALIAS_IZ: return "drift+alias+inv";
+        case S_R2C: return "r2c";
     }
     return "?";
 }
 
-double pass_bytes(const msm_ctx* c, int lop, int sop, int ns) {
+// algorithmic HBM bytes of one pass over `cells` complex elements per stream; share = streams that share one real
+// rho / phi value (2 for pair buffers, the whole CTA group in the summed-density mode)
+double pass_bytes(double cells, int lop, int sop, int ns, int share) {
     double per = 16.0;                                   // read the line
-    if (lop == L_KICK || lop == L_KICK_IX) per += 8.0;   // phi (16 B per pair of streams)
+    if (lop == L_KICK || lop == L_KICK_IX) per += 16.0 / share;   // phi
     if (sop != S_RHO_ONLY && sop != S_RHO_ONLY_FX && sop != S_MAX) per += 16.0;   // write the line
-    if (sop_is_rho(sop)) per += 8.0;                     // rho (16 B per pair)
+    if (sop_is_rho(sop)) per += 16.0 / share;            // rho
     if (sop == S_DRIFT_ALIAS_IZ) per += 16.0;            // second output
-    return per * (double)c->C * ns;
+    return per * cells * ns;
 }
 
 int prof_key(msm_ctx* c, const std::string& name) {
@@ -594,12 +646,15 @@ struct XformOps {
     double2* pbuf = nullptr;
     unsigned long long* maxbits = nullptr;
     double2* dst2 = nullptr;
+    bool dtab_shared = false;       // every stream of the launch has the same drift coefficient (summed density: one dt)
 };
 
 struct PassSpec {
     int axis;
     bool inv;
     int lop, sop;
+    int target = TG_MAIN;
+    int tile0 = 0, tile_end = -1;   // tile range of this launch (slab-pipelined launches); -1 = all
 };
 
 // a sequence of axis passes over the streams ids[0..ns): the first pass reads `src`, every pass writes `work`.
@@ -618,6 +673,7 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
     p.p_gstride = ctx->C;
     p.p_summed = o.p_summed;
     p.rho_accumulate = o.rho_accumulate;
+    p.dtab_shared = o.dtab_shared ? 1 : 0;
     p.ksq = ctx->ksq;
     p.four_pi2 = ctx->four_pi2;
     p.alias_k2_thresh = ctx->k2_max * ctx->cfg.k2_cutoff;   // simulation_object.rs:1265
@@ -627,9 +683,30 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
     p.alias_partial = ctx->alias_partial;
     p.maxbits = o.maxbits ? o.maxbits : ctx->maxbits;
     p.dst2 = o.dst2;
+    p.nyq = ctx->nyq;
+    p.wreal = ctx->wreal;
     for (size_t k = 0; k < seq.size(); ++k) {
-        const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop;
+        const int axis = seq[k].axis, lop = seq[k].lop, sop = seq[k].sop, tg = seq[k].target;
         const bool inv = seq[k].inv;
+        // grid view, transform length, kernels and tile heights of this pass
+        GridShape shape = main_shape(ctx);
+        pass_launcher_t launcher = ctx->launcher;
+        int N = ctx->n, TXL = ctx->TX;
+        p.twiddle = ctx->tw;
+        p.k2_fixed = 0.0;
+        if (tg == TG_HALF_X) {          // n/2-point passes along x over the real plane read as complex pairs
+            shape.nx = ctx->n / 2;
+            launcher = ctx->launcher_half;
+            N = ctx->n / 2;
+            TXL = ctx->TXH;
+            p.twiddle = ctx->tw_half;
+        } else if (tg == TG_HALF_YZ) {  // n-point passes along y / z over the half spectrum
+            shape.nx = ctx->n / 2;
+        } else if (tg == TG_NYQ) {      // the plane k_x = Nyquist: a linear 2-D grid over (k_y, k_z)
+            shape = GridShape{2, ctx->n, ctx->n, 0};
+            p.k2_fixed = ctx->h_ksq[ctx->n / 2];
+        }
+        const bool xl = axis == 0 && ctx->xl;
         // Streams per CTA group.  Only passes that touch the pair buffer need the whole group in one CTA (summed
         // coupling: rho accumulates over / phi is shared by all streams of the group); every other pass runs in pairs, so
         // that the two drift tables of a CTA stay resident in shared memory (fft_pass.cuh).
@@ -637,13 +714,15 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
                                sop == S_POISSON_INV || sop == S_MAX;
         p.gsz = pair_pass ? o.gsz : std::min(o.gsz, 2);
         const int groups = (ns + p.gsz - 1) / p.gsz;
-        const Geom g = make_geom(ctx, axis, (axis == 0 && ctx->xl) ? ctx->TX : ctx->T);
+        const Geom g = make_geom(shape, axis, xl ? TXL : ctx->T);
         const bool first = (k == 0);
         p.src = first ? src : work;
         p.src_by_sid = first ? src_by_sid : work_by_sid;
         p.dst = work;
         p.dst_by_sid = work_by_sid;
+        p.src_sstride = p.dst_sstride = tg == TG_MAIN ? ctx->C : shape.cells();
         p.axis = axis;
+        p.nx = shape.nx;
         p.tiles_inner = g.tiles_inner;
         p.outer_stride = g.outer;
         p.inner_stride = g.inner;
@@ -651,23 +730,26 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         p.astride = g.astride;
         p.olb = g.olb;
         p.alb = g.alb;
-        p.row_lb = ctx->lb;
+        p.row_lb = shape.lb;
         p.outer_lo = g.outer_lo;
         p.astride_lo = g.astride_lo;
         p.lvalid = g.lvalid;
         p.ntiles = g.ntiles;
-        char nm[96];
+        p.tile0 = seq[k].tile0;
+        p.tile_end = seq[k].tile_end < 0 ? g.ntiles : std::min(seq[k].tile_end, g.ntiles);
+        char nm[112];
         // consecutive tiles of one CTA must differ by inner_stride only: tiles_per_cta divides tiles_inner
         // (the contiguous axis has small tiles: more of them per CTA amortise the table preamble)
-        p.tiles_per_cta = (int)std::__gcd((long long)(axis == 0 && ctx->xl ? ctx->tiles_per_cta_x : ctx->tiles_per_cta),
-                                          (long long)g.tiles_inner);
+        p.tiles_per_cta = (int)std::__gcd((long long)(xl ? ctx->tiles_per_cta_x : ctx->tiles_per_cta), (long long)g.tiles_inner);
+        if (p.tile0 % p.tiles_per_cta) p.tiles_per_cta = (int)std::__gcd((long long)p.tiles_per_cta, (long long)p.tile0);
         p.l2_prefetch = ctx->l2_prefetch;
-        snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s,%s>", ctx->n, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop),
-                 axis == 0 ? "x" : axis == 1 ? "y" : "z");
+        snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s,%s%s>", N, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop),
+                 axis == 0 ? "x" : axis == 1 ? "y" : "z", tg == TG_MAIN ? "" : tg == TG_NYQ ? ",nyquist" : ",half");
+        const double frac = (double)(p.tile_end - p.tile0) / (double)g.ntiles;
         int rc;
         {
-            ProfScope ps(ctx, nm, pass_bytes(ctx, lop, sop, ns));
-            rc = ctx->launcher(inv, lop, sop, axis == 0 && ctx->xl, p, g.ntiles, groups, ctx->st);
+            ProfScope ps(ctx, nm, frac * pass_bytes((double)shape.cells(), lop, sop, ns, o.p_summed ? std::max(1, p.gsz) : 2));
+            rc = launcher(inv, lop, sop, xl, p, g.ntiles, groups, ctx->st);
         }
         ctx->launches++;
         if (rc == -1) return fail(ctx, MSM_E_ARG, std::string("no kernel instance for ") + nm);
@@ -730,17 +812,33 @@ std::vector<int> active_list(const msm_ctx* ctx, const int32_t* active) {
     return ids;
 }
 
-int allreduce_rho(msm_ctx* ctx) {
+// plane k (0 / 1) of the summed-density mode: n^d doubles inside pair buffer 0.  Plane 0 holds the density / potential
+// of the kick, plane 1 the density of the NEXT step's dt-potential (accumulated while later chunks still read phi)
+double2* real_plane(msm_ctx* ctx, int k) {
+    return reinterpret_cast<double2*>(reinterpret_cast<double*>(ctx->P) + (size_t)k * ctx->C);
+}
+
+// Sum the density over the ranks: `ncclAllReduce` of n^d doubles, in place.  With the real-field solve the REAL plane
+// goes over NVLink as it lies in memory (1 GiB at 512^3); the complex fallback (dims < 3) packs / unpacks the real parts.
+int allreduce_rho(msm_ctx* ctx, int plane) {
     if (ctx->cfg.nranks <= 1) return MSM_OK;
-    // rho is real: pack the real parts of pair buffer 0 into a scratch slot (8 B / cell), all-reduce n^d doubles over
-    // NVLink (1 GiB at 512^3 instead of the 2 GiB of the complex buffer), unpack
+    int rc;
+    if (ctx->real_solve) {
+        double* r = reinterpret_cast<double*>(real_plane(ctx, plane));
+        {
+            ProfScope ps(ctx, "nccl_allreduce_rho", 0.0);
+            rc = g_nccl.AllReduce(r, r, (size_t)ctx->C, NCCL_DOUBLE, NCCL_SUM, ctx->comm, ctx->st);
+        }
+        if (rc != 0)
+            return fail(ctx, MSM_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        return MSM_OK;
+    }
     double* packed = reinterpret_cast<double*>(ctx->Tscr);
     {
         ProfScope ps(ctx, "pack_rho", 24.0 * ctx->C);
         k_pack_real<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->P, packed, ctx->C);
     }
     ctx->launches++;
-    int rc;
     {
         ProfScope ps(ctx, "nccl_allreduce_rho", 0.0);
         rc = g_nccl.AllReduce(packed, packed, (size_t)ctx->C, NCCL_DOUBLE, NCCL_SUM, ctx->comm, ctx->st);
@@ -754,6 +852,44 @@ int allreduce_rho(msm_ctx* ctx) {
     ctx->launches++;
     if (cudaGetLastError() != cudaSuccess) return fail(ctx, MSM_E_CUDA, "pack/unpack of rho failed");
     return MSM_OK;
+}
+
+int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, int ns, const double2* src, int src_by_sid,
+               double2* work, int work_by_sid, const XformOps& o);
+
+// Real-field Poisson solve (summed-density mode, dims == 3), in place on one real plane of n^3 doubles:
+//   phi = F^-1[ c / (k^2 n^3) F[rho] ]          (simulation_object.rs:1066-1110; the reference transforms the real
+//                                                density as a full complex array, :1071, :1105)
+// The plane IS an array of n/2 x n x n complex pairs z[j] = rho[2j] + i rho[2j+1] along x.  R2C: an n/2-point pass +
+// S_R2C gives the half spectrum k_x = 0 .. n/2-1 in place and X[n/2] in the Nyquist plane; y and z run as ordinary
+// n-point passes over the half-spectrum grid (last forward + multiplier + first inverse fused: S_POISSON_INV), the
+// Nyquist plane as a 2-D grid at fixed k_x; C2R: L_C2R + an n/2-point inverse pass puts phi back as the real plane.
+// Half the bytes and flops of the complex solve: 5 x 16 = 80 B per cell instead of 160 (+ 48 of pack / unpack).
+int poisson_real(msm_ctx* ctx, int plane, bool max_only, unsigned long long* maxbits) {
+    const int id0 = 0;
+    XformOps o;
+    o.gsz = 1;
+    o.poisson_coef = ctx->cfg.poisson_coeff / pow((double)ctx->n, (double)ctx->dims);
+    o.maxbits = maxbits;
+    double2* r = real_plane(ctx, plane);
+    int rc;
+    std::vector<PassSpec> fwd{PassSpec{0, false, L_NONE, S_R2C, TG_HALF_X}, PassSpec{1, false, L_NONE, S_NONE, TG_HALF_YZ}};
+    std::vector<PassSpec> nyq{PassSpec{0, false, L_NONE, S_NONE, TG_NYQ}};
+    if (ctx->fuse) {
+        fwd.push_back(PassSpec{2, false, L_NONE, S_POISSON_INV, TG_HALF_YZ});
+        nyq.push_back(PassSpec{1, false, L_NONE, S_POISSON_INV, TG_NYQ});
+    } else {
+        fwd.push_back(PassSpec{2, false, L_NONE, S_POISSON, TG_HALF_YZ});
+        fwd.push_back(PassSpec{2, true, L_NONE, S_NONE, TG_HALF_YZ});
+        nyq.push_back(PassSpec{1, false, L_NONE, S_POISSON, TG_NYQ});
+        nyq.push_back(PassSpec{1, true, L_NONE, S_NONE, TG_NYQ});
+    }
+    fwd.push_back(PassSpec{1, true, L_NONE, S_NONE, TG_HALF_YZ});
+    nyq.push_back(PassSpec{0, true, L_NONE, S_NONE, TG_NYQ});
+    if ((rc = run_passes(ctx, fwd, &id0, 1, r, 0, r, 0, o))) return rc;
+    if ((rc = run_passes(ctx, nyq, &id0, 1, ctx->nyq, 0, ctx->nyq, 0, o))) return rc;
+    std::vector<PassSpec> back{PassSpec{0, true, L_C2R, max_only ? S_MAX : S_NONE, TG_HALF_X}};
+    return run_passes(ctx, back, &id0, 1, r, 0, r, 0, o);
 }
 
 // Poisson solve in place on `nbuf` pair buffers starting at ctx->P:  phi = F^-1[ c/(k^2 n^d) F[rho] ]
@@ -813,13 +949,16 @@ void invalidate_stream(msm_ctx* ctx, int s) {
 int fetch_pending_pmax(msm_ctx* ctx) {
     if (ctx->pmax_pending.empty()) return MSM_OK;
     const size_t n = ctx->pmax_pending.size();
-    if (cudaMemcpyAsync(ctx->h_scal + ctx->S + 2, ctx->maxbits, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->st) != cudaSuccess)
+    const bool shared = ctx->cfg.coupling == MSM_COUPLING_SUMMED;   // one potential for all streams: max(|re|, |im|) slots 0, 1
+    k_publish<<<1, 128, 0, ctx->st>>>(reinterpret_cast<const double*>(ctx->maxbits), ctx->h_scal + ctx->S + 2,
+                                      (int)(shared ? 2 : n));
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->st) != cudaSuccess)
         return fail(ctx, MSM_E_CUDA, "fetching max|phi| failed");
+    const double* h = ctx->h_scal + ctx->S + 2;
     for (size_t i = 0; i < n; ++i) {
         const int s = ctx->pmax_pending[i];
         if (s < 0) continue;   // invalidated since (invalidate_stream)
-        ctx->pmax_cache[s] = ctx->h_scal[ctx->S + 2 + i];
+        ctx->pmax_cache[s] = shared ? (h[0] != h[0] || h[1] != h[1] ? NAN : fmax(h[0], h[1])) : h[i];
         ctx->pmax_valid[s] = 1;
     }
     ctx->pmax_pending.clear();
@@ -978,32 +1117,59 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     CUC(cudaMalloc(&ctx->alias_out, sizeof(double) * ctx->S));
     CUC(cudaMalloc(&ctx->maxbits, sizeof(unsigned long long) * (ctx->S + 2)));
     CUC(cudaMalloc(&ctx->scratch_small, sizeof(double) * 4096));
-    CUC(cudaMallocHost(&ctx->h_dtab, sizeof(double2) * n * ctx->S));
-    CUC(cudaMallocHost(&ctx->h_scal, sizeof(double) * 2 * (ctx->S + 2)));   // [0, S+2): alias / max ; [S+2, ..): eager max
+    CUC(cudaHostAlloc(&ctx->h_coef, sizeof(double) * ctx->S, cudaHostAllocMapped));
+    CUC(cudaHostAlloc(&ctx->h_ids, sizeof(int) * ctx->S, cudaHostAllocMapped));
+    CUC(cudaHostAlloc(&ctx->h_scal, sizeof(double) * 2 * (ctx->S + 2), cudaHostAllocMapped));   // [0, S+2): alias / max ; [S+2, ..): eager max
     ctx->bytes = cb * (ctx->S + chunk + npair) + sizeof(double2) * n * (ctx->S + 1) + sizeof(double) * n +
                  sizeof(double) * (size_t)ctx->S * (glast.ntiles + 1) + 8 * (ctx->S + 2) + 8 * 4096;
     CUC(cudaMemsetAsync(ctx->alias_out, 0, sizeof(double) * ctx->S, ctx->st));
     CUC(cudaMemsetAsync(ctx->alias_partial, 0, sizeof(double) * (size_t)ctx->S * glast.ntiles, ctx->st));
     {
         // per-stage twiddle tables [k - 1][nu] = exp(-2 pi i k L nu / n)   (fft_pass.cuh: plan_tw_offset)
-        std::vector<double2> tw(n, make_double2(1.0, 0.0));
-        int rad[4];
-        const int nst = plan_radices(n, rad);
-        int off = 0, L = 1;
-        for (int q = 0; q + 1 < nst; ++q) {
-            const int M = n / (L * rad[q]);
-            for (int k = 1; k < rad[q]; ++k)
-                for (int nu = 0; nu < M; ++nu) {
-                    const long long j = (long long)k * L * nu;   // < n
-                    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
-                    tw[off + (k - 1) * M + nu] = make_double2((double)cosl(a), (double)sinl(a));
-                }
-            off += (rad[q] - 1) * M;
-            L *= rad[q];
-        }
+        auto stage_twiddles = [](int len) {
+            std::vector<double2> tw(len, make_double2(1.0, 0.0));
+            int rad[4];
+            const int nst = plan_radices(len, rad);
+            int off = 0, L = 1;
+            for (int q = 0; q + 1 < nst; ++q) {
+                const int M = len / (L * rad[q]);
+                for (int k = 1; k < rad[q]; ++k)
+                    for (int nu = 0; nu < M; ++nu) {
+                        const long long j = (long long)k * L * nu;   // < len
+                        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)len;
+                        tw[off + (k - 1) * M + nu] = make_double2((double)cosl(a), (double)sinl(a));
+                    }
+                off += (rad[q] - 1) * M;
+                L *= rad[q];
+            }
+            return tw;
+        };
+        const std::vector<double2> tw = stage_twiddles(n);
         CUC(cudaMemcpyAsync(ctx->tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->st));
         CUC(cudaMemcpyAsync(ctx->ksq, ctx->h_ksq.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
         CUC(cudaStreamSynchronize(ctx->st));
+        // Real-field Poisson solve for the summed density (one real field per rank; the independent mode gets the same
+        // saving by packing two streams into one complex solve).  MSM_B200_REAL=0 keeps the complex solve (A/B timing).
+        ctx->real_solve = cfg->coupling == MSM_COUPLING_SUMMED && cfg->dims == 3 && n >= 16 && ctx->xl;
+        if (const char* e = getenv("MSM_B200_REAL")) ctx->real_solve = ctx->real_solve && atoi(e) != 0;
+        if (ctx->real_solve) {
+            const int nh = n / 2;
+            ctx->launcher_half = get_pass_launcher(nh);
+            ctx->TXH = ctx->xl ? plan_tx(nh) : plan_T(nh);
+            const std::vector<double2> twh = stage_twiddles(nh);
+            std::vector<double2> wr(nh);
+            for (int k = 0; k < nh; ++k) {
+                const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+                wr[k] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+            CUC(cudaMalloc(&ctx->tw_half, sizeof(double2) * nh));
+            CUC(cudaMalloc(&ctx->wreal, sizeof(double2) * nh));
+            CUC(cudaMalloc(&ctx->nyq, sizeof(double2) * (size_t)n * n));
+            ctx->bytes += sizeof(double2) * ((size_t)n * n + 2 * nh);
+            CUC(cudaMemcpyAsync(ctx->tw_half, twh.data(), sizeof(double2) * nh, cudaMemcpyHostToDevice, ctx->st));
+            CUC(cudaMemcpyAsync(ctx->wreal, wr.data(), sizeof(double2) * nh, cudaMemcpyHostToDevice, ctx->st));
+            CUC(cudaStreamSynchronize(ctx->st));
+        }
     }
     if (cfg->coupling == MSM_COUPLING_SUMMED && cfg->nranks > 1) {
         if (!cfg->nccl_unique_id) return bail(MSM_E_ARG, "nranks > 1 requires nccl_unique_id");
@@ -1032,6 +1198,9 @@ void msm_destroy(msm_ctx* ctx) {
     cudaFree(ctx->Tscr);
     cudaFree(ctx->P);
     cudaFree(ctx->tw);
+    cudaFree(ctx->tw_half);
+    cudaFree(ctx->wreal);
+    cudaFree(ctx->nyq);
     cudaFree(ctx->dtab);
     cudaFree(ctx->ksq);
     cudaFree(ctx->alias_partial);
@@ -1042,7 +1211,8 @@ void msm_destroy(msm_ctx* ctx) {
     cudaFree(ctx->ens_psik);
     cudaFree(ctx->ens_psi2);
     cudaFree(ctx->ens_psik2);
-    if (ctx->h_dtab) cudaFreeHost(ctx->h_dtab);
+    if (ctx->h_coef) cudaFreeHost(ctx->h_coef);
+    if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->dtab_done) cudaEventDestroy(ctx->dtab_done);
     for (int i = 0; i < 2; ++i) {
@@ -1383,9 +1553,17 @@ static int density_from_psik(msm_ctx* ctx, const int* ids, int ns, bool summed, 
     // un-normalised inverse passes: |psi|^2 = |u|^2 / n^d
     o.rho_coef = ctx->cfg.density_prefactor / n3 / (summed ? (double)sg : 1.0);
     o.gsz = summed ? ns : 2;
-    o.p_summed = summed ? 1 : 0;
+    o.p_summed = summed ? (ctx->real_solve ? 2 : 1) : 0;
+    if (summed && ctx->real_solve) o.pbuf = real_plane(ctx, 1);   // the dt-potential lives in plane 1
     o.rho_accumulate = accumulate ? 1 : 0;
     return run_transform(ctx, true, ids, ns, ctx->X, 1, ctx->Tscr, 0, o);
+}
+
+// summed mode: potential of the density accumulated in plane 1 (real-field solve) / pair buffer 0 (complex fallback)
+static int summed_potential(msm_ctx* ctx, bool max_only, unsigned long long* maxbits) {
+    int rc = allreduce_rho(ctx, 1);
+    if (rc) return rc;
+    return ctx->real_solve ? poisson_real(ctx, 1, max_only, maxbits) : poisson(ctx, 1, max_only, maxbits);
 }
 
 static int potential_max_of(msm_ctx* ctx, const std::vector<int>& ids, double* out) {
@@ -1427,15 +1605,17 @@ static int potential_max_of(msm_ctx* ctx, const std::vector<int>& ids, double* o
             rc = density_from_psik(ctx, &ids[i], ns, true, i > 0);
             if (rc) return rc;
         }
-        rc = allreduce_rho(ctx);
-        if (rc) return rc;
-        rc = poisson(ctx, 1, true, ctx->maxbits);
+        rc = summed_potential(ctx, true, ctx->maxbits);
         if (rc) return rc;
     }
-    CU(cudaMemcpyAsync(ctx->h_scal, ctx->maxbits, sizeof(double) * ids.size(), cudaMemcpyDeviceToHost, ctx->st));
+    k_publish<<<1, 128, 0, ctx->st>>>(reinterpret_cast<const double*>(ctx->maxbits), ctx->h_scal,
+                                      (int)std::max<size_t>(2, ids.size()));
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->st));
+    const double* h = ctx->h_scal;
+    const double shared_max = (h[0] != h[0] || h[1] != h[1]) ? NAN : fmax(h[0], h[1]);   // summed: max(|re|, |im|) slots
     for (size_t i = 0; i < ids.size(); ++i) {
-        out[ids[i]] = summed ? ctx->h_scal[0] : ctx->h_scal[i];
+        out[ids[i]] = summed ? shared_max : ctx->h_scal[i];
         ctx->pmax_cache[ids[i]] = out[ids[i]];
         ctx->pmax_valid[ids[i]] = 1;
     }
@@ -1474,6 +1654,7 @@ int msm_get_potential(msm_ctx* ctx, int32_t s, double* phi) {
         int id = s;
         rc = density_from_psik(ctx, &id, 1, false, false);
         if (rc) return rc;
+        rc = poisson(ctx, 1, false, nullptr);
     } else {
         std::vector<int> ids = active_list(ctx, nullptr);
         rc = ensure_kspace(ctx, ids);
@@ -1483,13 +1664,15 @@ int msm_get_potential(msm_ctx* ctx, int32_t s, double* phi) {
             rc = density_from_psik(ctx, &ids[i], ns, true, i > 0);
             if (rc) return rc;
         }
-        rc = allreduce_rho(ctx);
-        if (rc) return rc;
+        rc = summed_potential(ctx, false, nullptr);
     }
-    rc = poisson(ctx, 1, false, nullptr);
     if (rc) return rc;
     double* stage = reinterpret_cast<double*>(ctx->Tscr);
-    k_extract<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->P, stage, ctx->C, ctx->n, ctx->lb, 0);
+    if (summed && ctx->real_solve)   // phi is a real plane already
+        k_extract_real<<<grid_for(ctx->C), 256, 0, ctx->st>>>(reinterpret_cast<const double*>(real_plane(ctx, 1)), stage, ctx->C,
+                                                              ctx->n, ctx->lb);
+    else
+        k_extract<<<grid_for(ctx->C), 256, 0, ctx->st>>>(ctx->P, stage, ctx->C, ctx->n, ctx->lb, 0);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(phi, stage, sizeof(double) * (size_t)ctx->C, cudaMemcpyDeviceToHost, ctx->st));
@@ -1500,7 +1683,8 @@ int msm_get_potential(msm_ctx* ctx, int32_t s, double* phi) {
 int msm_read_alias(msm_ctx* ctx, double* alias_mass) {
     if (!ctx || !alias_mass) return fail(ctx, MSM_E_ARG, "msm_read_alias: bad argument");
     CU(cudaSetDevice(ctx->cfg.device));
-    CU(cudaMemcpyAsync(ctx->h_scal, ctx->alias_out, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->st));
+    k_publish<<<1, 128, 0, ctx->st>>>(ctx->alias_out, ctx->h_scal, ctx->S);
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->st));
     for (int s = 0; s < ctx->S; ++s) alias_mass[s] = ctx->h_scal[s];
     return MSM_OK;
@@ -1517,39 +1701,47 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
     const bool summed = ctx->cfg.coupling == MSM_COUPLING_SUMMED;
 
     // per-axis drift tables: exp(-i c k^2) = prod_axes exp(-i c (2 pi k_m)^2); n^(-1/2) per pass = unitary scale
-    CU(cudaEventSynchronize(ctx->dtab_done));
-    const double sc = 1.0 / sqrt((double)n);
-    for (int s : ids) {
-        double2* t = ctx->h_dtab + (size_t)s * n;
-        for (int m = 0; m < n; ++m) {
-            const double th = -drift[s] * (ctx->h_ksq[m] * ctx->four_pi2);
-            t[m] = make_double2(sc * cos(th), sc * sin(th));
-        }
+    CU(cudaEventSynchronize(ctx->dtab_done));   // the previous step's build kernel has read the coefficients
+    bool same_drift = true;
+    for (size_t i = 0; i < ids.size(); ++i) {
+        ctx->h_ids[i] = ids[i];
+        ctx->h_coef[ids[i]] = drift[ids[i]];
+        same_drift = same_drift && drift[ids[i]] == drift[ids[0]];
     }
-    CU(cudaMemcpyAsync(ctx->dtab, ctx->h_dtab, sizeof(double2) * n * ctx->S, cudaMemcpyHostToDevice, ctx->st));
+    k_build_dtab<<<(int)ids.size(), 128, 0, ctx->st>>>(ctx->h_coef, ctx->h_ids, ctx->ksq, ctx->dtab, n, ctx->four_pi2,
+                                                     1.0 / sqrt((double)n));
+    ctx->launches++;
+    CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->dtab_done, ctx->st));
 
     const int sg = ctx->cfg.n_streams_global > 0 ? ctx->cfg.n_streams_global : ctx->S;
+    const bool real = summed && ctx->real_solve;
     auto drift_inverse = [&](const int* cid, int ns, bool accumulate) {
         XformOps o;   // psi_k * drift -> psi (in place), rho out
         o.lop_each = L_DRIFT;
         o.sop_last = S_RHO_KEEP;
         o.rho_coef = ctx->cfg.density_prefactor / (summed ? (double)sg : 1.0);
         o.gsz = summed ? ns : 2;
-        o.p_summed = summed ? 1 : 0;
+        o.p_summed = summed ? (real ? 2 : 1) : 0;
+        if (real) o.pbuf = real_plane(ctx, 0);
         o.rho_accumulate = accumulate ? 1 : 0;
+        o.dtab_shared = summed && same_drift;
         return run_transform(ctx, true, cid, ns, ctx->X, 1, ctx->X, 1, o);
     };
-    auto kick_forward = [&](const int* cid, int ns) {
+    auto kick_forward = [&](const int* cid, int ns, bool start_next_potential) {
         XformOps o;   // psi * kick -> psi_k * drift (in place), alias partials out
         double kk[MAX_CHUNK];
         for (int i = 0; i < ns; ++i) kk[i] = kick[cid[i]];
         o.lop_first = L_KICK;
         o.sop_each = S_DRIFT;
-        o.sop_last = S_DRIFT_ALIAS;
+        // the last pass can also run the first inverse pass of the next dt-potential into the scratch slots
+        o.sop_last = start_next_potential ? S_DRIFT_ALIAS_IZ : S_DRIFT_ALIAS;
+        o.dst2 = ctx->Tscr;
         o.kick = kk;
         o.gsz = summed ? ns : 2;
-        o.p_summed = summed ? 1 : 0;
+        o.p_summed = summed ? (real ? 2 : 1) : 0;
+        if (real) o.pbuf = real_plane(ctx, 0);
+        o.dtab_shared = summed && same_drift;
         return run_transform(ctx, false, cid, ns, ctx->X, 1, ctx->X, 1, o);
     };
     for (int s : ids) ctx->pmax_valid[s] = 0;
@@ -1593,18 +1785,53 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
             if ((rc = drift_inverse(&ids[i], ns, false))) return rc;
             if ((rc = poisson(ctx, (ns + 1) / 2, false, nullptr))) return rc;
-            if ((rc = kick_forward(&ids[i], ns))) return rc;
+            if ((rc = kick_forward(&ids[i], ns, false))) return rc;
+        }
+    } else if (real) {
+        // Summed density, real-field solve (dims == 3).  rho accumulates over the local streams into real plane 0, is
+        // summed over the ranks in place, and one replicated half-spectrum solve leaves phi in the same plane.  While the
+        // chunks are kicked (all reading plane 0), their last forward pass already starts the NEXT step's dt-potential
+        // (first inverse pass into the scratch slots); its density accumulates into plane 1, which is reduced and solved
+        // for max|phi| only.  Per step and rank: 2 x 8 B/cell over NVLink and 2 x 80 B/cell of replicated solve.
+        const int d = ctx->dims;
+        const bool eager = ctx->fuse;
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            if ((rc = drift_inverse(&ids[i], ns, i > 0))) return rc;
+        }
+        if ((rc = allreduce_rho(ctx, 0))) return rc;
+        if ((rc = poisson_real(ctx, 0, false, nullptr))) return rc;
+        for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
+            const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
+            if ((rc = kick_forward(&ids[i], ns, eager))) return rc;
+            if (eager) {   // rest of psi_k -> psi of this chunk (scratch slots), |psi|^2 into plane 1
+                XformOps o;
+                o.gsz = ns;
+                o.p_summed = 2;
+                o.pbuf = real_plane(ctx, 1);
+                o.rho_accumulate = i > 0;
+                o.rho_coef = ctx->cfg.density_prefactor / pow((double)n, (double)d) / (double)sg;   // un-normalised passes
+                std::vector<PassSpec> seq;
+                for (int a = d - 2; a >= 1; --a) seq.push_back(PassSpec{a, true, L_NONE, S_NONE});
+                seq.push_back(PassSpec{0, true, L_NONE, S_RHO_ONLY});
+                if ((rc = run_passes(ctx, seq, &ids[i], ns, ctx->Tscr, 0, ctx->Tscr, 0, o))) return rc;
+            }
+        }
+        if (eager && ids.size() == (size_t)ctx->S) {   // the shared potential needs every stream's density
+            CU(cudaMemsetAsync(ctx->maxbits, 0, sizeof(unsigned long long) * (ctx->S + 2), ctx->st));
+            if ((rc = summed_potential(ctx, true, ctx->maxbits))) return rc;
+            ctx->pmax_pending = ids;
         }
     } else {
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
             if ((rc = drift_inverse(&ids[i], ns, i > 0))) return rc;
         }
-        if ((rc = allreduce_rho(ctx))) return rc;
+        if ((rc = allreduce_rho(ctx, 0))) return rc;
         if ((rc = poisson(ctx, 1, false, nullptr))) return rc;
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
-            if ((rc = kick_forward(&ids[i], ns))) return rc;
+            if ((rc = kick_forward(&ids[i], ns, false))) return rc;
         }
     }
     {
@@ -1614,7 +1841,8 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
     ctx->launches++;
     CU(cudaGetLastError());
     if (alias_mass) {
-        CU(cudaMemcpyAsync(ctx->h_scal, ctx->alias_out, sizeof(double) * ctx->S, cudaMemcpyDeviceToHost, ctx->st));
+        k_publish<<<1, 128, 0, ctx->st>>>(ctx->alias_out, ctx->h_scal, ctx->S);
+        CU(cudaGetLastError());
         if ((rc = fetch_pending_pmax(ctx))) return rc;   // same sync
         CU(cudaStreamSynchronize(ctx->st));
         for (int s : ids) alias_mass[s] = ctx->h_scal[s];

@@ -41,7 +41,8 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         configured = true;
     }
-    dim3 grid((ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta, groups, 1);
+    (void)ntiles;
+    dim3 grid((p.tile_end - p.tile0 + p.tiles_per_cta - 1) / p.tiles_per_cta, groups, 1);
     kern<<<grid, tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>(), smem, st>>>(p);
     return (int)cudaPeekAtLastError();
 }
@@ -76,6 +77,15 @@ int MSM_CAT(launch_pass_, MSM_FFT_N)(bool inv, int lop, int sop, bool xl, const 
     CASE(false, L_KICK_IX, S_DRIFT)
     CASE(false, L_NONE, S_DRIFT_ALIAS_IZ)
 #undef CASE
+    // real-field Poisson solve of the summed-density mode: R2C / C2R (run as n/2-point passes along x)
+#define CASE_X(I, L, S) \
+    if (inv == I && lop == L && sop == S) return launch<I, L, S, true>(p, ntiles, groups, st);
+    if (xl) {
+        CASE_X(false, L_NONE, S_R2C)
+        CASE_X(true, L_C2R, S_NONE)
+        CASE_X(true, L_C2R, S_MAX)
+    }
+#undef CASE_X
     return -1;
 }
 

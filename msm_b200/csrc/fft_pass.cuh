@@ -30,8 +30,11 @@ enum LoadOp {
     L_NONE = 0,
     L_DRIFT = 1,
     L_KICK = 2,
-    L_KICK_IX = 3   // L_KICK, but the pair buffer holds phi BEFORE its last inverse pass: that pass runs here, on the
+    L_KICK_IX = 3,  // L_KICK, but the pair buffer holds phi BEFORE its last inverse pass: that pass runs here, on the
                     // same lines, so phi never travels to HBM in real space
+    L_C2R = 4       // half-spectrum line X[0..N-1] (+ X[N] from the Nyquist plane) of a REAL line of 2N values ->
+                    // Z[k] = (X[k] + conj X[N-k]) + i conj(W_2N^k) (X[k] - conj X[N-k]); the inverse N-point transform of
+                    // Z is then z[j] = x[2j] + i x[2j+1]: the real line, stored as it lies in memory
 };
 enum StoreOp {
     S_NONE = 0,         // plain store
@@ -46,9 +49,12 @@ enum StoreOp {
     S_RHO_ONLY_FX = 10, // lines: the pair buffer receives rho after the first pass of the Poisson solve
     S_DRIFT_ALIAS_IZ = 11,  // S_DRIFT_ALIAS, then the INVERSE transform of the stored psi_k into dst2 (first pass of the
                             // next dt-potential)
-    S_POISSON_INV = 8   // S_POISSON, then the INVERSE transform of the same lines, then store: the last forward
+    S_POISSON_INV = 8,  // S_POISSON, then the INVERSE transform of the same lines, then store: the last forward
                         // and first inverse pass of the Poisson solve share their tile, so the k-space potential
                         // never travels to HBM
+    S_R2C = 12          // the line was a REAL line of 2N values read as z[j] = x[2j] + i x[2j+1]: turn Z = F_N[z] into the
+                        // half spectrum X[k] = (Z[k] + conj Z[N-k]) / 2 - i W_2N^k (Z[k] - conj Z[N-k]) / 2, k < N, stored
+                        // in place; X[N] (real, like X[0]) goes to the Nyquist plane
 };
 
 struct PassParams {
@@ -78,11 +84,18 @@ struct PassParams {
     long long p_gstride;
     int p_summed;                         // 1: all streams accumulate into buffer 0 component x
     int rho_accumulate;                   // summed mode: add to what is already in the buffer
+    int dtab_shared;                      // all streams of the launch use the drift factors of the first one
     const double* ksq;                    // (k_m)^2 = (m_signed / (n dx))^2, n entries  (utils/fft.rs:100-120)
     double four_pi2, alias_k2_thresh, poisson_coef, rho_coef, scale;
     double* alias_partial;                // [n_streams][ntiles] by stream id
     int ntiles;
     unsigned long long* maxbits;          // [2 * buffers]: bit patterns of non-negative doubles
+    // real-field Poisson solve of the summed-density mode (S_R2C / L_C2R and the passes over the half spectrum)
+    int nx;                               // extent of the fastest dimension (n, or n / 2 on the half-spectrum grid)
+    double k2_fixed;                      // (k_x)^2 of the Nyquist plane (a 2-D grid at fixed k_x), else 0
+    double2* nyq;                         // Nyquist plane [row c2][row c1]: X[N] of every line
+    const double2* wreal;                 // W_2N^k = exp(-2 pi i k / 2N), k < N
+    int tile0, tile_end;                  // this launch covers tiles [tile0, tile_end) (slab-pipelined launches)
     int tiles_per_cta;                    // one-tile kernel: consecutive tiles walked by one CTA (L2 prefetch depth)
     int zero;                             // always 0; only the compiler does not know (see data_dependent)
     int l2_prefetch;                      // pull the next item's tile into L2 while the current one computes
@@ -424,9 +437,13 @@ template <int N, int EV> __device__ __forceinline__ void outputs_to_inputs(doubl
 }
 // exchange region in double2 units; single-stage plans (N <= 8) have no exchange, but L_KICK_IX parks phi_a there
 template <int N, int LOP, bool XL> constexpr int exchange_elems() {   // (E * threads = N * T for every E)
-    return Plan<N>::NS > 1 ? (XL ? (N + N / 8) : N) * tile_T<N, XL>()
+    // (L_C2R and its counterpart S_R2C pair every element with its mirror image through this buffer, even when the
+    //  transform itself has a single stage; the launcher sizes S_R2C kernels with LOP = L_C2R)
+    return (Plan<N>::NS > 1 || LOP == L_C2R) ? (XL ? (N + N / 8) : N) * tile_T<N, XL>()
                            : (LOP == L_KICK_IX ? (Plan<N>::E * tile_threads<N, XL>() + 1) / 2 : 0);
 }
+constexpr bool uses_wreal(int lop, int sop) { return lop == L_C2R || sop == S_R2C; }
+template <int LOP, int SOP> constexpr int exch_lop() { return uses_wreal(LOP, SOP) ? (int)L_C2R : LOP; }
 // Small read-only tables live in shared memory behind the exchange buffer: an L1 hit still costs a long-scoreboard
 // wait at every use (the kernels have no registers to batch such loads), an LDS does not.
 //   twiddles [N] double2 | (k_m)^2 [N] double (k^2 consumers) | drift factors [2][N] double2 (drift operators):
@@ -434,10 +451,11 @@ template <int N, int LOP, bool XL> constexpr int exchange_elems() {   // (E * th
 //   coupling) reload slot 0 for every item.
 constexpr bool uses_dtab(int lop, int sop) { return lop == L_DRIFT || sop == S_DRIFT || sop_is_alias(sop); }
 template <int N, int LOP, int SOP> constexpr int table_elems() {   // double2 units
-    return (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0) + (uses_dtab(LOP, SOP) ? 2 * N : 0);
+    return (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0) + (uses_dtab(LOP, SOP) ? 2 * N : 0) +
+           (uses_wreal(LOP, SOP) ? N : 0);
 }
 template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {   // E * threads = N * T for every E
-    return sizeof(double2) * (exchange_elems<N, LOP, XL>() + table_elems<N, LOP, SOP>()) +
+    return sizeof(double2) * (exchange_elems<N, exch_lop<LOP, SOP>(), XL>() + table_elems<N, LOP, SOP>()) +
            (uses_stash<LOP, SOP>() ? sizeof(double) * Plan<N>::E * tile_threads<N, XL>() : 0);
 }
 
@@ -456,12 +474,14 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     extern __shared__ double2 sm[];
     // per-thread stash [E][THREADS] behind the exchange buffer: holds the partner stream's rho / phi so that the
     // pair buffer is always accessed as full 16-byte words
-    double* stash = reinterpret_cast<double*>(sm + exchange_elems<N, LOP, XL>() + table_elems<N, LOP, SOP>());
+    constexpr int EXCH = exchange_elems<N, exch_lop<LOP, SOP>(), XL>();
+    double* stash = reinterpret_cast<double*>(sm + EXCH + table_elems<N, LOP, SOP>());
     __shared__ double red[2][32];
     __shared__ unsigned long long redm[2][32];
-    double2* tws = sm + exchange_elems<N, LOP, XL>();
+    double2* tws = sm + EXCH;
     double* ks = reinterpret_cast<double*>(tws + (kTwSmem ? N : 0));
     double2* dts = tws + (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0);
+    double2* wrs = dts + (uses_dtab(LOP, SOP) ? 2 * N : 0);   // W_2N^k, k < N (real-field passes)
     const double2* tw_base = p.twiddle;
     if constexpr (kTwSmem) {
         for (int i = threadIdx.x; i < N; i += THREADS) tws[i] = p.twiddle[i];
@@ -470,7 +490,10 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     if constexpr (sop_needs_k2(SOP)) {
         for (int i = threadIdx.x; i < N; i += THREADS) ks[i] = p.ksq[i];
     }
-    if constexpr (kTwSmem || sop_needs_k2(SOP)) __syncthreads();
+    if constexpr (uses_wreal(LOP, SOP)) {
+        for (int i = threadIdx.x; i < N; i += THREADS) wrs[i] = p.wreal[i];
+    }
+    if constexpr (kTwSmem || sop_needs_k2(SOP) || uses_wreal(LOP, SOP)) __syncthreads();
     unsigned long long run_max = 0ull, run_max2 = 0ull;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
     int item_parity = 0;
 
@@ -531,17 +554,17 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
 
     // the host makes tiles_per_cta a divisor of tiles_inner: consecutive tiles of one CTA differ by inner_stride
     const int tstride = (int)p.inner_stride, loff = la * (int)p.lstride;
-    int origin = tile_origin(blockIdx.x * p.tiles_per_cta) - tstride;
+    int origin = tile_origin(p.tile0 + blockIdx.x * p.tiles_per_cta) - tstride;
     for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
-    const int tile = blockIdx.x * p.tiles_per_cta + ti;
-    if (tile >= p.ntiles) break;
+    const int tile = p.tile0 + blockIdx.x * p.tiles_per_cta + ti;
+    if (tile >= p.tile_end) break;
     origin += tstride;
     const int base = origin + loff;
 
     // coordinates of this line along the two non-pass axes (only the k^2 consumers need them)
     double k_a = 0.0, k_b = 0.0;
     int c0 = 0, c1 = 0, c2 = 0;
-    if constexpr (sop_needs_k2(SOP)) {
+    if constexpr (sop_needs_k2(SOP) || uses_wreal(LOP, SOP)) {
         const int n = p.n;
         if (p.axis == 0) {
             const int line = tile * T + l;   // row index in the (blocked) device layout, see core.cu blk_index
@@ -551,15 +574,18 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             c2 = tile / p.tiles_inner;
             c0 = (tile % p.tiles_inner) * T + l;
         } else {
-            const int line = tile * T + l;
-            c1 = line / n;
-            c0 = line % n;
+            const int line = tile * T + l;   // (nx = n except on the half-spectrum grid of the real-field solve)
+            c1 = line / p.nx;
+            c0 = line % p.nx;
         }
         if (!lv) c0 = c1 = c2 = 0;
+    }
+    if constexpr (sop_needs_k2(SOP)) {
         // spec_grid sums ((k0^2 + k1^2) + k2^2) * (2 pi)^2 with dim 0 the fastest axis (utils/fft.rs:141-160)
-        // one expression for all axes: x + 0 == x exactly, and every term is >= 0
+        // one expression for all axes: x + 0 == x exactly, and every term is >= 0.  k2_fixed is (k_x)^2 of the Nyquist
+        // plane of the real-field solve (a 2-D grid over (k_y, k_z) at fixed k_x), 0 everywhere else.
         if (p.axis == 2) k_a = ks[c0] + ks[c1], k_b = 0.0;
-        else if (p.axis == 1) k_a = ks[c0], k_b = ks[c2];
+        else if (p.axis == 1) k_a = p.k2_fixed + ks[c0], k_b = ks[c2];
         else k_a = ks[c1], k_b = ks[c2];
     }
     auto k2_of = [&](int e) -> double {
@@ -603,9 +629,11 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
         double2* __restrict__ pbl = pb + base;
         const double2* dt = dts;   // this item's drift factors in shared memory
         if constexpr (uses_dtab(LOP, SOP)) {
-            const bool resident = p.gsz <= 2;   // both streams of the group stay in their slots for all tiles
-            if (resident) dt = dts + q * N;
-            if (!resident || ti == 0) {
+            // both streams of the group stay in their slots for all tiles; a group with one common drift coefficient
+            // (summed density: one dt for all streams) needs a single table for all items
+            const bool resident = p.gsz <= 2 || p.dtab_shared;
+            if (resident && !p.dtab_shared) dt = dts + q * N;
+            if (!resident || (ti == 0 && (q == 0 || !p.dtab_shared))) {
                 if (!resident) __syncthreads();   // the previous item still reads slot 0
                 for (int i = threadIdx.x; i < N; i += THREADS) const_cast<double2*>(dt)[i] = __ldg(&p.dtab[(long long)s * N + i]);
                 __syncthreads();
@@ -668,6 +696,32 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
                 }
             }
         }
+        if constexpr (LOP == L_C2R) {
+            // half spectrum of a real line of 2N values -> spectrum of z[j] = x[2j] + i x[2j+1]; every element meets its
+            // mirror image X[N - k] through the (idle) exchange buffer, X[N] comes from the Nyquist plane
+            double2 xn = make_double2(0.0, 0.0);
+            if (t == 0) xn = p.nyq[((long long)li * p.n + c2) * p.n + c1];
+#pragma unroll
+            for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                for (int n = 0; n < R0; ++n) sm[sm_index<N, XL>(n * M0 + t + NT * c, l)] = v[c * R0 + n];
+            }
+            exchange_barrier<N, XL, E>(l);
+#pragma unroll
+            for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    const int e = n * M0 + t + NT * c;
+                    double2 pr = sm[sm_index<N, XL>((N - e) & (N - 1), l)];
+                    if (c == 0 && n == 0 && t == 0) pr = xn;
+                    const double2 x = v[c * R0 + n], w = wrs[e];
+                    const double2 a = make_double2(x.x + pr.x, x.y - pr.y), b = make_double2(x.x - pr.x, x.y + pr.y);
+                    const double2 mm = cmul(make_double2(w.x, -w.y), b);
+                    v[c * R0 + n] = make_double2(a.x - mm.y, a.y + mm.x);
+                }
+            }
+            exchange_barrier<N, XL, E>(l);   // everyone has read its mirror image before the first stage scatters
+        }
         if constexpr (LOP == L_KICK_IX) {
             const double* phia = reinterpret_cast<const double*>(sm);
 #pragma unroll
@@ -688,9 +742,14 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
                     double ph;
                     double* slot = &stash[(c * R0 + n) * THREADS + tid];
                     if (q == 0) {
-                        const double2 pp = pbl[eoff(c + n * NB0)];
-                        ph = pp.x;
-                        if (!last_of_group) *slot = p.p_summed ? pp.x : pp.y;
+                        if (p.p_summed == 2) {   // shared potential as a REAL plane (summed density, real-field solve)
+                            ph = reinterpret_cast<const double*>(pb)[base + eoff(c + n * NB0)];
+                            if (!last_of_group) *slot = ph;
+                        } else {
+                            const double2 pp = pbl[eoff(c + n * NB0)];
+                            ph = pp.x;
+                            if (!last_of_group) *slot = p.p_summed ? pp.x : pp.y;
+                        }
                     } else {
                         ph = *slot;
                     }
@@ -720,6 +779,15 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             run_stages<N, !INV, XL, 0>(v, sm, t, l, data_dependent(tw_base, v[0].x, p.zero));
         }
 
+        if constexpr (SOP == S_R2C) {
+            // Z[k] of this line into the (idle) exchange buffer: every output needs Z[N - k] as well
+#pragma unroll
+            for (int c = 0; c < NBL; ++c) {
+#pragma unroll
+                for (int k = 0; k < RL; ++k) sm[sm_index<N, XL>(t + NT * c + LL * k, l)] = v[c * RL + k];
+            }
+            exchange_barrier<N, XL, E>(l);
+        }
         // ---- store (last-stage output order) ----
         fresh_offsets(v[0].x);
         double acc = 0.0;
@@ -734,6 +802,17 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
                 if constexpr (SOP == S_SCALE) {
                     x.x *= p.scale;
                     x.y *= p.scale;
+                }
+                if constexpr (SOP == S_R2C) {
+                    const double2 zp = sm[sm_index<N, XL>((N - e) & (N - 1), l)], w = wrs[e];
+                    const double2 a = make_double2(x.x + zp.x, x.y - zp.y), b = make_double2(x.x - zp.x, x.y + zp.y);
+                    const double2 mm = cmul(w, b);
+                    if (c == 0 && k == 0 && t == 0) {   // k = 0: X[0] = Re Z + Im Z and X[N] = Re Z - Im Z, both real
+                        if (lv) p.nyq[((long long)li * p.n + c2) * p.n + c1] = make_double2(x.x - x.y, 0.0);
+                        x = make_double2(x.x + x.y, 0.0);
+                    } else {
+                        x = make_double2(0.5 * (a.x + mm.y), 0.5 * (a.y - mm.x));
+                    }
                 }
                 if constexpr (SOP == S_DRIFT || sop_is_alias(SOP)) {
                     const double2 w = dt[e];
@@ -771,13 +850,17 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
                     } else {
                         const double sum = (q == 0) ? rho : *slot + rho;
                         if (!last_of_group) *slot = sum;
+                        else if (p.p_summed == 2) {   // the summed density is kept as a REAL plane (8 B / cell)
+                            double* rp = reinterpret_cast<double*>(pb) + base;
+                            if (lv) rp[off] = p.rho_accumulate ? rp[off] + sum : sum;
+                        }
                         else pair = make_double2(p.rho_accumulate ? pbl[off].x + sum : sum, 0.0);   // (stored by lv lines only)
                     }
                     if (SOP != S_RHO_ONLY && SOP != S_RHO_ONLY_FX) {
                         dst[off] = x;
                     }
                     if (FX) v[c * RL + k] = pair;               // transformed below, after psi has been stored
-                    else if (last_of_group && lv) pbl[off] = pair;
+                    else if (last_of_group && lv && p.p_summed != 2) pbl[off] = pair;
                 }
                 if constexpr (!sop_is_rho(SOP) && SOP != S_MAX) {
                     dst[off] = x;
@@ -786,6 +869,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             }
         }
 
+        if constexpr (SOP == S_R2C) exchange_barrier<N, XL, E>(l);   // mirror images read before the next item scatters
         if constexpr (SOP == S_RHO_KEEP_FX || SOP == S_RHO_ONLY_FX) {
             // first (x) pass of the Poisson solve on the finished pair rho_a + i rho_b, same lines: forward transform
             if (last_of_group) {

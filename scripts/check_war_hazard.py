@@ -61,7 +61,7 @@ def source_regs(text):
     t = strip_pred(text)
     op, _, rest = t.partition(" ")
     regs = set()
-    toks = re.findall(r"R(\d+)(\.64)?", rest)
+    toks = re.findall(r"(?<![A-Za-z])R(\d+)(\.64)?", rest)      # (not the R of a uniform register: desc[UR12])
     is_store = op.startswith("ST")
     skip_first = not (is_store or op.startswith(NO_DEST))
     for k, (r, wide) in enumerate(toks):

@@ -422,6 +422,38 @@ def test_summed_mode_matches_oracle(name, nstreams):
     sim.close()
 
 
+@pytest.mark.parametrize("size,nstreams,chunk,lb,real", [(32, 3, 2, 0, 1), (64, 2, 0, 0, 1), (64, 5, 4, 2, 1), (128, 2, 0, 3, 1),
+                                                         (32, 3, 2, 0, 0)])
+def test_summed_mode_real_field_solve(monkeypatch, size, nstreams, chunk, lb, real):
+    """The shared potential of the summed-density mode is solved on the REAL density: n/2-point R2C / C2R passes along x,
+    half-spectrum y / z passes, Nyquist plane (n/2 = 16 .. 64 here, 256 in test_gpu_headline.py), with the blocked
+    device layout forced as well; real = 0 runs the complex fallback for comparison.  Trajectory, dt, max|phi| and the
+    potential itself against the oracle ensemble."""
+    monkeypatch.setenv("MSM_B200_LB", str(lb))
+    monkeypatch.setenv("MSM_B200_REAL", str(real))
+    ps = oracle_streams("spherical-tophat", size, limit=nstreams)
+    psi0s = [initial_wavefunction(p) for p in ps]
+    ens = o.SummedEnsemble(ps[0], psi0s)
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=nstreams, coupling=m.COUPLING_SUMMED, chunk_streams=chunk)
+    for i, a in enumerate(psi0s):
+        sim.set_psi(i, a)
+    for k in range(3):
+        sim.update()
+        ens.update()
+        st = sim.state(nstreams - 1)
+        assert abs(st.dt - ens.head.last_dt) <= 1e-13 * ens.head.last_dt
+        assert abs(st.potential_max - ens.head.last_potential_max) <= 1e-12 * ens.head.last_potential_max
+    for i in range(nstreams):
+        assert rel_l2(sim.get_psi(i), ens.streams[i].psi) < 1e-10
+        assert alias_close(sim.state(i).alias_mass, ens.streams[i].last_alias_mass)
+    ens._potential()
+    assert rel_l2(sim.grid.get_potential(0), ens.head.phi.real) < 1e-12
+    sim.update()                                     # the cached max|phi| survived the potential download
+    ens.update()
+    assert abs(sim.state(0).dt - ens.head.last_dt) <= 1e-13 * ens.head.last_dt
+    sim.close()
+
+
 def test_summed_mode_with_identical_streams_equals_independent():
     p = oracle_streams("spherical-tophat")[-1]
     psi0 = initial_wavefunction(p)
