@@ -26,6 +26,7 @@
 
 #include "../../include/msm_b200.h"
 #include "fft_pass.cuh"
+#include "fft_tma.h"
 
 namespace msm {
 #define DECL(N) int launch_pass_##N(bool, int, int, bool, const PassParams&, int, int, cudaStream_t);
@@ -475,6 +476,9 @@ struct msm_ctx {
     // real-field Poisson solve of the summed-density mode (dims == 3, n >= 16): the real plane of n^3 doubles IS a grid
     // of n/2 x n x n complex pairs (x[2j], x[2j+1]); R2C / C2R run as n/2-point passes over it, the y / z passes as
     // n-point passes over the half spectrum, and X[n/2] of every x line lives in a small Nyquist plane (n x n complex)
+    // TMA variant of the plain strided 512-point pass (fft_tma.cu), MSM_B200_TMA=1: tensor maps [array][axis - 1]
+    bool tma = false;
+    TmaMap tma_map[3][2];
     bool real_solve = false;
     pass_launcher_t launcher_half = nullptr;
     double2 *tw_half = nullptr, *wreal = nullptr, *nyq = nullptr;
@@ -747,7 +751,28 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
                  axis == 0 ? "x" : axis == 1 ? "y" : "z", tg == TG_MAIN ? "" : tg == TG_NYQ ? ",nyquist" : ",half");
         const double frac = (double)(p.tile_end - p.tile0) / (double)g.ntiles;
         int rc;
-        {
+        const double2* arrays[3] = {ctx->X, ctx->Tscr, ctx->P};
+        int which = -1;
+        for (int a = 0; a < 3; ++a)
+            if (p.src == arrays[a] && p.dst == arrays[a]) which = a;
+        if (ctx->tma && tg == TG_MAIN && lop == L_NONE && sop == S_NONE && axis > 0 && which >= 0 && p.tile0 == 0 &&
+            p.tile_end == g.ntiles) {
+            // experiment: the same pass through cp.async.bulk.tensor (fft_tma.cu), one CTA column per stream
+            TmaPassParams tp{};
+            tp.twiddle = ctx->tw;
+            for (int i = 0; i < ns; ++i) tp.slot[i] = p.src_by_sid ? ids[i] : i;
+            tp.axis = axis;
+            tp.ntiles = g.ntiles;
+            tp.tiles_inner = g.tiles_inner;
+            tp.tiles_per_cta = p.tiles_per_cta;
+            tp.lb = ctx->lb;
+            // cp.async.bulk.prefetch.tensor of later items measured SLOWER (1.29 x DRAM reads: prefetch and load both miss)
+            tp.l2_prefetch = getenv("MSM_B200_TMA_PF") ? atoi(getenv("MSM_B200_TMA_PF")) : 0;
+            strncat(nm, "[tma]", sizeof nm - strlen(nm) - 1);
+            ProfScope ps(ctx, nm, pass_bytes((double)shape.cells(), lop, sop, ns, 2));
+            tp.ns = ns;
+            rc = tma_launch_pass(inv, &ctx->tma_map[which][axis - 1], tp, ctx->num_sms, ctx->st);
+        } else {
             ProfScope ps(ctx, nm, frac * pass_bytes((double)shape.cells(), lop, sop, ns, o.p_summed ? std::max(1, p.gsz) : 2));
             rc = launcher(inv, lop, sop, xl, p, g.ntiles, groups, ctx->st);
         }
@@ -1148,6 +1173,17 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
         CUC(cudaMemcpyAsync(ctx->tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, ctx->st));
         CUC(cudaMemcpyAsync(ctx->ksq, ctx->h_ksq.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
         CUC(cudaStreamSynchronize(ctx->st));
+        if (const char* e = getenv("MSM_B200_TMA")) {
+            if (atoi(e) != 0 && n == 512 && cfg->dims == 3 && ctx->lb > 0) {
+                void* bases[3] = {ctx->X, ctx->Tscr, ctx->P};
+                const int slots[3] = {ctx->S, chunk, npair};
+                ctx->tma = true;
+                for (int a = 0; a < 3 && ctx->tma; ++a)
+                    for (int ax = 1; ax <= 2 && ctx->tma; ++ax)
+                        if (tma_make_map(&ctx->tma_map[a][ax - 1], bases[a], n, ctx->lb, slots[a], ax) != 0) ctx->tma = false;
+                if (!ctx->tma) return bail(MSM_E_CUDA, "MSM_B200_TMA=1: cuTensorMapEncodeTiled failed");
+            }
+        }
         // Real-field Poisson solve for the summed density (one real field per rank; the independent mode gets the same
         // saving by packing two streams into one complex solve).  MSM_B200_REAL=0 keeps the complex solve (A/B timing).
         ctx->real_solve = cfg->coupling == MSM_COUPLING_SUMMED && cfg->dims == 3 && n >= 16 && ctx->xl;

@@ -33,7 +33,7 @@ int launch(const PassParams& p, int ntiles, int groups, cudaStream_t st) {
         cudaFuncAttributes fa;
         int pct = (int)cudaSharedmemCarveoutDefault;
         if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
-            const size_t need = (smem + fa.sharedSizeBytes + 1024) * (size_t)tile_minb<N, XL, plan_E<N, LOP, SOP, XL>()>();
+            const size_t need = (smem + fa.sharedSizeBytes + 1024) * (size_t)kernel_minb<N, LOP, SOP, XL>();
             pct = (int)((need * 100 + 227 * 1024 - 1) / (227 * 1024)) + 1;
             if (pct > 100) pct = 100;
         }

@@ -156,8 +156,17 @@ template <int N, bool XL, int EV = Plan<N>::E> constexpr int tile_minb() {
 #ifndef MSM_WIDE_DAI
 #define MSM_WIDE_DAI 1
 #endif
+// `poisson+inv` (two transforms + the k-space multiplier per tile): MSM_WIDE_PI = 1 gives it the same wide plan,
+// MSM_PI_NOSTASH = 1 evaluates c / k^2 where it is used instead of parking 8 multipliers per thread in shared memory
+#ifndef MSM_WIDE_PI
+#define MSM_WIDE_PI 0
+#endif
+#ifndef MSM_PI_NOSTASH
+#define MSM_PI_NOSTASH 1
+#endif
 template <int N, int LOP, int SOP, bool XL> constexpr int plan_E() {
-    return (MSM_WIDE_DAI && N == 512 && !XL && SOP == 11 /* S_DRIFT_ALIAS_IZ */) ? 16 : Plan<N>::E;
+    return (N == 512 && !XL && ((MSM_WIDE_DAI && SOP == 11 /* S_DRIFT_ALIAS_IZ */) || (MSM_WIDE_PI && SOP == 8 /* S_POISSON_INV */)))
+               ? 16 : Plan<N>::E;
 }
 
 template <int N> constexpr int plan_L(int q) {   // product of radices of stages < q
@@ -359,9 +368,15 @@ template <int N, bool XL, int EV> __device__ __forceinline__ void exchange_barri
 #define MSM_TW_SMEM 1
 #endif
 constexpr bool kTwSmem = MSM_TW_SMEM != 0;
-template <int N, bool INV, bool XL, int Q, int EV>
+// TEAM > 0: the transform is run by a TEAM of that many threads inside a larger CTA (fft_tma.cu); its exchanges then
+// synchronise on the named barrier `team_bar` instead of the CTA-wide one.
+template <int N, bool XL, int EV, int TEAM> __device__ __forceinline__ void stage_barrier(int l, int team_bar) {
+    if constexpr (TEAM > 0) asm volatile("bar.sync %0, %1;" ::"r"(team_bar), "n"(TEAM) : "memory");
+    else exchange_barrier<N, XL, EV>(l);
+}
+template <int N, bool INV, bool XL, int Q, int EV, int TEAM = 0>
 __device__ __forceinline__ void run_stages(double2 (&v)[EV], double2* sm, int t, int l,
-                                           const double2* __restrict__ tw) {
+                                           const double2* __restrict__ tw, int team_bar = 0) {
     using PL = Plan<N>;
     constexpr int E = EV, NT = N / EV;
     constexpr int R = PL::R[Q];
@@ -388,7 +403,7 @@ __device__ __forceinline__ void run_stages(double2 (&v)[EV], double2* sm, int t,
                 sm[sm_index<N, XL>((kappa + L * k) * M + nu, l)] = x;
             }
         }
-        exchange_barrier<N, XL, EV>(l);
+        stage_barrier<N, XL, EV, TEAM>(l, team_bar);
         constexpr int R2 = PL::R[Q + 1];
         constexpr int L2 = L * R;
         constexpr int M2 = N / (L2 * R2);
@@ -400,14 +415,14 @@ __device__ __forceinline__ void run_stages(double2 (&v)[EV], double2* sm, int t,
 #pragma unroll
             for (int n = 0; n < R2; ++n) v[c * R2 + n] = sm[sm_index<N, XL>(kappa * (M2 * R2) + n * M2 + nu, l)];
         }
-        exchange_barrier<N, XL, EV>(l);
-        run_stages<N, INV, XL, Q + 1>(v, sm, t, l, tw);
+        stage_barrier<N, XL, EV, TEAM>(l, team_bar);
+        run_stages<N, INV, XL, Q + 1, EV, TEAM>(v, sm, t, l, tw, team_bar);
     }
 }
 
 template <int LOP, int SOP> constexpr bool uses_stash() {
-    return LOP == L_KICK || LOP == L_KICK_IX || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY || SOP == S_POISSON_INV ||
-           SOP == S_RHO_KEEP_FX || SOP == S_RHO_ONLY_FX;
+    return LOP == L_KICK || LOP == L_KICK_IX || SOP == S_RHO_KEEP || SOP == S_RHO_ONLY ||
+           (SOP == S_POISSON_INV && !MSM_PI_NOSTASH) || SOP == S_RHO_KEEP_FX || SOP == S_RHO_ONLY_FX;
 }
 constexpr bool sop_is_rho(int sop) {
     return sop == S_RHO_KEEP || sop == S_RHO_ONLY || sop == S_RHO_KEEP_FX || sop == S_RHO_ONLY_FX;
@@ -450,6 +465,16 @@ template <int LOP, int SOP> constexpr int exch_lop() { return uses_wreal(LOP, SO
 //   slot q of the drift table belongs to stream q of the CTA's group; groups of more than two streams (summed
 //   coupling) reload slot 0 for every item.
 constexpr bool uses_dtab(int lop, int sop) { return lop == L_DRIFT || sop == S_DRIFT || sop_is_alias(sop); }
+// Resident CTAs a kernel instance is compiled for.  Contiguous-axis kernels without drift tables need 26-34 KiB of shared
+// memory instead of 50-54: MSM_XL_MINB_NODT lets them run more, smaller-register CTAs (A/B: profiles/README.md).
+#ifndef MSM_XL_MINB_NODT
+#define MSM_XL_MINB_NODT MSM_XL_MINB
+#endif
+template <int N, int LOP, int SOP, bool XL> constexpr int kernel_minb() {
+    constexpr int EV = plan_E<N, LOP, SOP, XL>();
+    if (EV == Plan<N>::E && XL && tile_T<N, XL>() != Plan<N>::T && !uses_dtab(LOP, SOP)) return MSM_XL_MINB_NODT;
+    return tile_minb<N, XL, EV>();
+}
 template <int N, int LOP, int SOP> constexpr int table_elems() {   // double2 units
     return (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0) + (uses_dtab(LOP, SOP) ? 2 * N : 0) +
            (uses_wreal(LOP, SOP) ? N : 0);
@@ -461,7 +486,7 @@ template <int N, int LOP, int SOP, bool XL> constexpr size_t pass_smem_bytes() {
 
 template <int N, bool INV, int LOP, int SOP, bool XL>
 __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>(),
-                                  tile_minb<N, XL, plan_E<N, LOP, SOP, XL>()>()) fft_pass_kernel(const PassParams p) {
+                                  kernel_minb<N, LOP, SOP, XL>()) fft_pass_kernel(const PassParams p) {
     using PL = Plan<N>;
     constexpr int E = plan_E<N, LOP, SOP, XL>(), T = tile_T<N, XL>(), NT = N / E, THREADS = NT * T;
     constexpr int R0 = PL::R[0];
@@ -605,7 +630,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             }
         }
     }
-    if constexpr (SOP == S_POISSON_INV) {
+    if constexpr (SOP == S_POISSON_INV && !MSM_PI_NOSTASH) {
         // c / (k^2 n^d) of this thread's 8 outputs, once per tile and while registers are free; parked in the stash
 #pragma unroll
         for (int c = 0; c < NBL; ++c) {
@@ -770,7 +795,12 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             for (int c = 0; c < NBL; ++c) {
 #pragma unroll
                 for (int k = 0; k < RL; ++k) {
+#if MSM_PI_NOSTASH
+                    const double k2 = k2_of(t + NT * c + LL * k);
+                    const double m = (k2 == 0.0) ? 0.0 : p.poisson_coef * fast_rcp(k2);
+#else
                     const double m = stash[(c * RL + k) * THREADS + tid];
+#endif
                     v[c * RL + k].x *= m;
                     v[c * RL + k].y *= m;
                 }

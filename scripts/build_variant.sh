@@ -14,5 +14,5 @@ for n in 2 4 8 16 32 64 128 256 512 1024; do
 done
 $NV -c core.cu -o $D/core.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libmsm_b200_$NAME.so $OBJS $D/core.o build/sim.o -ldl -lpthread
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libmsm_b200_$NAME.so $OBJS $D/core.o build/fft_tma.o build/sim.o -ldl -lpthread
 echo built msm_b200/libmsm_b200_$NAME.so

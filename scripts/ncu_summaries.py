@@ -27,9 +27,9 @@ METRICS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thr
            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio"]
-LOPS = {0: "none", 1: "drift", 2: "kick", 3: "invx+kick"}
+LOPS = {0: "none", 1: "drift", 2: "kick", 3: "invx+kick", 4: "c2r"}
 SOPS = {0: "none", 1: "scale", 2: "drift", 3: "drift+alias", 4: "psi+rho", 5: "rho", 6: "poisson", 7: "max",
-        8: "poisson+inv", 9: "psi+rho+fwdx", 10: "rho+fwdx", 11: "drift+alias+inv"}
+        8: "poisson+inv", 9: "psi+rho+fwdx", 10: "rho+fwdx", 11: "drift+alias+inv", 12: "r2c"}
 
 
 def pretty(name):

@@ -141,3 +141,35 @@ def test_two_steps_match_oracle_at_256():
         assert abs(st.potential_max - ref.last_potential_max) <= 1e-12 * ref.last_potential_max
     assert rel_l2(sim.get_psi(0), ref.psi) < 1e-10
     sim.close()
+
+
+def test_tma_variant_of_the_plain_pass_is_bit_identical_512(monkeypatch):
+    """MSM_B200_TMA=1 routes the plain strided 512-point passes (Poisson y passes, dt-potential y pass) through the
+    cp.async.bulk.tensor kernel of fft_tma.cu: same butterflies, same order -> the same bits after two steps."""
+    p = gaussian_params(512)
+    osim = o.SimulationObject(p, np.zeros((2, 2, 2), dtype=np.complex128))
+    out = []
+    for tma in ("0", "1"):
+        monkeypatch.setenv("MSM_B200_TMA", tma)
+        ctx = m.Context(3, 512, 3, p.dx, osim.density_prefactor(), osim.poisson_coeff(), p.k2_cutoff, chunk_streams=4)
+        ctx.ic_cold_gauss(0, [15.0] * 3, [9.0] * 3)
+        for s in (1, 2):
+            ctx.ic_copy(s, 0)
+        for s in range(3):
+            ctx.sample_perturbation(s, "Wigner", 31 + s, 1e6)
+        ctx.profile_enable(True)
+        res = []
+        for _ in range(2):
+            pm = ctx.potential_max()
+            dt = p.cfl * np.pi * p.hbar_ / pm
+            res.append((pm, ctx.step(dt * p.hbar_ / 4.0, dt / p.hbar_)))
+        names = [r["name"] for r in ctx.profile_read()]
+        assert any("[tma]" in nm for nm in names) == (tma == "1")
+        res.append([ctx.get_psik(s) for s in (0, 2)])
+        out.append(res)
+        ctx.close()
+    a, b = out
+    for k in range(2):
+        assert np.array_equal(a[k][0], b[k][0]) and np.array_equal(a[k][1], b[k][1])
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y)
