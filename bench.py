@@ -76,16 +76,19 @@ def parse():
     return ap.parse_args()
 
 
+N_TOT_SAMPLER = 1e10        # Wigner noise with n_tot = 1e10
+
+
 def workload_params(size):
     """examples/gaussian-overdensity-mft.toml resolved (tests/golden/configs.json holds the same numbers)."""
     import msm_b200 as m
     hbar_ = 0.02
+    # (particle_mass only fixes n_tot = total_mass / particle_mass of the sampler: 1e10, SURVEY section 8d config 5)
     return m.SimulationParameters(axis_length=30.0, final_sim_time=400.0, cfl=0.02, num_data_dumps=200,
-                                  total_mass=1e10, particle_mass=1.757e-90 / hbar_, hbar_=hbar_, k2_cutoff=0.95,
+                                  total_mass=1e10, particle_mass=1e10 / N_TOT_SAMPLER, hbar_=hbar_, k2_cutoff=0.95,
                                   alias_threshold=0.02, dims=3, size=size, time=0.0, cosmology=None)
 
 
-N_TOT_SAMPLER = 1e10        # SURVEY section 8d config (5): Wigner noise with n_tot = 1e10
 
 
 class ClockSampler:
@@ -440,7 +443,28 @@ def main():
                "update() per stream, download of every stream's final psi as re/im planes) inside the timed region; "
                "transfers of neighbouring stream groups overlap the step kernels"}
         assert sim.state(n_local - 1).n_steps == args.steps and np.isfinite(renp[:16]).all()
-    sim.close()
+        sim.close()
+        if coupling == m.COUPLING_INDEPENDENT:
+            # second flavour: the same loop with the initial conditions built on the device from (IC spec, seed) -- what
+            # the reference's own `new_from_params` does -- so that only the dump half crosses PCIe
+            sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=coupling)
+            g = sim.grid
+            g.ic_cold_gauss(0, [15.0] * 3, [10.0] * 3)
+            g.ic_store(0)
+            g.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            sim.run_streams_seeded(ids, "Wigner", [rank * n_local + s + 1 for s in ids], [renp] * n_local, [imnp] * n_local,
+                                   max_updates=args.steps)
+            sec2 = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            assert sim.state(n_local - 1).n_steps == args.steps and np.isfinite(renp[:16]).all()
+            e2e["seeded"] = {"value": cells * n_total * args.steps / sec2, "unit": "cell-updates/s", "seconds": sec2,
+                             "h2d_bytes_per_step": int(20 * n_local + 12 * n_local),
+                             "d2h_bytes_per_step": int(16 * cells * n_local / args.steps + 16 * n_local),
+                             "what": "msm_sim_run_streams_seeded: un-sampled IC saved on the device + seeded Wigner sampler "
+                                     "per stream (device), K x update(), download of every stream's final psi"}
+            sim.close()
 
     # ---- the reference's CPU algorithm beside it (rank 0, N = 1 only) ------------------------------------------
     cpu = None

@@ -179,6 +179,11 @@ int msm_ic_spherical_tophat(msm_ctx* ctx, int32_t stream, double axis_length, do
  * reference (it hard-codes a 3-D phase array, ics.rs:401-406). */
 int msm_ic_cold_gauss_kspace(msm_ctx* ctx, int32_t stream, const double* mean, const double* std, uint64_t phase_seed);
 int msm_ic_copy(msm_ctx* ctx, int32_t dst_stream, int32_t src_stream);
+/* Keep one wavefunction aside / put it back into a stream (device-to-device, enqueued on the compute stream): the
+ * un-sampled initial condition that every stream of a TOML starts from before its seed is applied
+ * (`new_from_params`, simulation_object.rs:404-435 builds it anew for every stream). */
+int msm_ic_store(msm_ctx* ctx, int32_t stream);
+int msm_ic_load(msm_ctx* ctx, int32_t stream);
 int msm_sample_perturbation(msm_ctx* ctx, int32_t stream, int32_t scheme, uint64_t seed, double n_tot);
 
 /* Ensemble statistics over streams (restates the reductions of the `synthesizer` crate,
@@ -190,6 +195,10 @@ int msm_sample_perturbation(msm_ctx* ctx, int32_t stream, int32_t scheme, uint64
  * msm_ensemble_get downloads one field (0 psi, 1 psi2, 2 psik, 3 psik2) as re / im planes in the host's linear layout;
  * psi2 and psik2 are real (the reference writes an all-zero imaginary file); either pointer may be NULL. */
 int msm_ensemble_accumulate(msm_ctx* ctx, const int32_t* active);
+/* Sum the four accumulators over the ranks (ncclAllReduce, in place; every rank ends up with the totals): the
+ * multi-rank form of the `+=` into the shared accumulators of synthesizer/src/lib.rs:217-240.  Needs a context
+ * created with nranks > 1 and an nccl_unique_id (any coupling mode); a no-op for nranks == 1. */
+int msm_ensemble_allreduce(msm_ctx* ctx);
 int msm_ensemble_get(msm_ctx* ctx, int32_t field, double* re, double* im);
 
 /* Per-kernel timing (CUDA events around every launch on the context's stream).  msm_profile_read returns up to
@@ -284,6 +293,15 @@ int msm_sim_update_streams(msm_sim* sim, const int32_t* subset);
  * MSM_E_ALIASING after finishing the others.  Independent coupling only. */
 int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const double* const* psi_in,
                         double* const* re_out, double* const* im_out, uint64_t max_updates);
+/* The same loop with the initial conditions built ON THE DEVICE: every listed stream starts from the
+ * wavefunction saved by msm_ic_store (the un-sampled initial condition: build it once with msm_ic_* / msm_set_psi on any
+ * stream of msm_sim_ctx(sim), then msm_ic_store) and receives `sample_quantum_perturbation` (ics.rs:434-648) with
+ * seeds[i] and the given MSM_SCHEME_* (n_tot = total_mass / particle_mass); seeds[i] == MSM_SEED_NONE leaves the stream
+ * un-sampled (the trailing mean-field run of `SimulationIter`, utils/io.rs:214-240).  Nothing but scalars crosses PCIe on
+ * the way in, so an 8-rank run is not limited by the host's upload bandwidth. */
+#define MSM_SEED_NONE UINT64_MAX
+int msm_sim_run_streams_seeded(msm_sim* sim, int32_t n, const int32_t* streams, int32_t scheme, const uint64_t* seeds,
+                               double* const* re_out, double* const* im_out, uint64_t max_updates);
 /* The stream groups msm_sim_run_streams forms for n streams with the given launch chunk: writes the group boundaries
  * (groups + 1 entries, bounds[0] = 0, last = n; at most cap entries) and returns the number of groups.  Host logic only. */
 int msm_run_groups(int32_t n, int32_t chunk, int32_t* bounds, int32_t cap);

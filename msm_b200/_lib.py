@@ -17,6 +17,7 @@ MSM_E_ARG, MSM_E_CUDA, MSM_E_NCCL, MSM_E_ALIASING, MSM_E_NAN, MSM_E_STATE, MSM_E
 COUPLING_INDEPENDENT, COUPLING_SUMMED = 0, 1
 SCHEME_NONE, SCHEME_POISSON, SCHEME_WIGNER, SCHEME_HUSIMI = 0, 1, 2, 3
 SCHEMES = {"Poisson": SCHEME_POISSON, "Wigner": SCHEME_WIGNER, "Husimi": SCHEME_HUSIMI}
+SEED_NONE = 2 ** 64 - 1
 
 
 class MsmError(RuntimeError):
@@ -102,8 +103,11 @@ PROTOTYPES = {
     "msm_ic_spherical_tophat": (C.c_int, [_vp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "msm_ic_cold_gauss_kspace": (C.c_int, [_vp, C.c_int32, _dp, _dp, C.c_uint64]),
     "msm_ic_copy": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "msm_ic_store": (C.c_int, [_vp, C.c_int32]),
+    "msm_ic_load": (C.c_int, [_vp, C.c_int32]),
     "msm_sample_perturbation": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_double]),
     "msm_ensemble_accumulate": (C.c_int, [_vp, _ip]),
+    "msm_ensemble_allreduce": (C.c_int, [_vp]),
     "msm_ensemble_get": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "msm_profile_enable": (C.c_int, [_vp, C.c_int32]),
     "msm_profile_read": (C.c_int, [_vp, C.POINTER(MsmProfileRecord), C.c_int32, _ip]),
@@ -119,6 +123,8 @@ PROTOTYPES = {
     "msm_sim_update": (C.c_int, [_vp]),
     "msm_sim_update_streams": (C.c_int, [_vp, _ip]),
     "msm_sim_run_streams": (C.c_int, [_vp, C.c_int32, _ip, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.c_uint64]),
+    "msm_sim_run_streams_seeded": (C.c_int, [_vp, C.c_int32, _ip, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(_dp),
+                                           C.POINTER(_dp), C.c_uint64]),
     "msm_run_groups": (C.c_int, [C.c_int32, C.c_int32, _ip, C.c_int32]),
     "msm_sim_not_finished": (C.c_int, [_vp]),
     "msm_sim_state": (C.c_int, [_vp, C.c_int32, C.POINTER(MsmStreamState)]),

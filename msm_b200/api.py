@@ -226,15 +226,25 @@ class Context:
     def ic_copy(self, dst: int, src: int) -> None:
         self._chk(lib.msm_ic_copy(self.handle, dst, src))
 
+    def ic_store(self, stream: int) -> None:
+        """keep the stream's wavefunction aside (the un-sampled IC every stream starts from)"""
+        self._chk(lib.msm_ic_store(self.handle, stream))
+
+    def ic_load(self, stream: int) -> None:
+        self._chk(lib.msm_ic_load(self.handle, stream))
+
     def sample_perturbation(self, stream: int, scheme: str, seed: int, n_tot: float) -> None:
         self._chk(lib.msm_sample_perturbation(self.handle, stream, _lib.SCHEMES[scheme], int(seed), float(n_tot)))
 
     # ensemble statistics (SURVEY row f-3: the synthesizer's stream reductions, on the device)
-    def ensemble_sums(self, active=None) -> Dict[str, np.ndarray]:
+    def ensemble_sums(self, active=None, allreduce: bool = False) -> Dict[str, np.ndarray]:
         """SUMS over the selected streams of psi, |psi|^2, psi_k (un-normalised DFT), |psi_k|^2
-        (synthesizer/src/main.rs:63-93); divide by the global stream count for the synthesizer's means."""
+        (synthesizer/src/main.rs:63-93); divide by the global stream count for the synthesizer's means.
+        allreduce: also sum over the ranks of the communicator (ncclAllReduce of the four grids, in place)."""
         keep, ptr = self._active(active)
         self._chk(lib.msm_ensemble_accumulate(self.handle, ptr))
+        if allreduce:
+            self._chk(lib.msm_ensemble_allreduce(self.handle))
         out = {}
         for field, name in enumerate(("psi", "psi2", "psik", "psik2")):
             re = np.empty(self.shape, dtype=np.float64)
@@ -396,6 +406,31 @@ class SimulationObject:
             assert a is None or a.size == 2 * self.grid.cells
         code = lib.msm_sim_run_streams(self.handle, n, ids.ctypes.data_as(_ip), ptrs(psi_in), ptrs(re_out), ptrs(im_out),
                                        int(max_updates))
+        if code == _lib.MSM_E_ALIASING:
+            if raise_on_alias:
+                raise FourierAliasing(code, lib.msm_sim_last_error(self.handle).decode())
+            return
+        check(code, self.handle, sim=True)
+
+    def run_streams_seeded(self, streams: Sequence[int], scheme: Optional[str], seeds: Sequence[Optional[int]],
+                           re_out: Optional[Sequence[Optional[np.ndarray]]] = None,
+                           im_out: Optional[Sequence[Optional[np.ndarray]]] = None, max_updates: int = 0,
+                           raise_on_alias: bool = True) -> None:
+        """run_streams with the initial conditions built on the device: the wavefunction saved by `grid.ic_store`
+        + `sample_quantum_perturbation` with seeds[i] (None = un-sampled).  Only scalars cross PCIe on the way in."""
+        n = len(streams)
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+        sd = np.array([_lib.SEED_NONE if s is None else int(s) for s in seeds], dtype=np.uint64)
+        assert sd.size == n
+
+        def ptrs(arrs):
+            if arrs is None:
+                return None
+            assert len(arrs) == n
+            return (_dp * n)(*[_f64(a.reshape(-1)) if a is not None else None for a in arrs])
+        code = lib.msm_sim_run_streams_seeded(self.handle, n, ids.ctypes.data_as(_ip), _lib.SCHEMES.get(scheme, 0),
+                                              sd.ctypes.data_as(C.POINTER(C.c_uint64)), ptrs(re_out), ptrs(im_out),
+                                              int(max_updates))
         if code == _lib.MSM_E_ALIASING:
             if raise_on_alias:
                 raise FourierAliasing(code, lib.msm_sim_last_error(self.handle).decode())

@@ -431,6 +431,8 @@ struct msm_ctx {
     double* h_scal = nullptr;    // pinned + mapped, 2*(S+2) doubles: written by k_publish, read by the host after a sync
     unsigned long long* maxbits = nullptr;
     double* scratch_small = nullptr;  // 4096 doubles
+    double2* ic_base = nullptr;                        // msm_ic_store / msm_ic_load: one saved wavefunction
+    char ic_base_in_k = 0;
     double2 *ens_psi = nullptr, *ens_psik = nullptr;   // ensemble sums (row f-3), allocated on first use
     double *ens_psi2 = nullptr, *ens_psik2 = nullptr;
     std::vector<char> in_k, has_psi;
@@ -480,6 +482,12 @@ struct msm_ctx {
     bool tma = false;
     TmaMap tma_map[3][2];
     bool real_solve = false;
+    // slab pipeline of the density all-reduce (nranks > 1): the last x pass that completes rho is launched in `ar_slabs`
+    // row ranges; as soon as a range is final its ncclAllReduce runs on comm_st (high priority) while the next range is
+    // still being computed, and the R2C pass of the Poisson solve starts range by range as the sums arrive
+    int ar_slabs = 1;
+    cudaStream_t comm_st = nullptr;
+    cudaEvent_t ev_slab[8] = {}, ev_ar[8] = {};
     pass_launcher_t launcher_half = nullptr;
     double2 *tw_half = nullptr, *wreal = nullptr, *nyq = nullptr;
     int TXH = 0;           // contiguous-axis tile height of the n/2-point kernels
@@ -611,17 +619,19 @@ struct ProfScope {
     msm_ctx* c;
     ProfEvent ev{};
     bool on;
-    ProfScope(msm_ctx* c_, const std::string& name, double bytes) : c(c_), on(c_->prof) {
+    cudaStream_t s;
+    ProfScope(msm_ctx* c_, const std::string& name, double bytes, cudaStream_t stream = nullptr)
+        : c(c_), on(c_->prof), s(stream ? stream : c_->st) {
         if (!on) return;
         ev.key = prof_key(c, name);
         ev.bytes = bytes;
         cudaEventCreate(&ev.a);
         cudaEventCreate(&ev.b);
-        cudaEventRecord(ev.a, c->st);
+        cudaEventRecord(ev.a, s);
     }
     ~ProfScope() {
         if (!on) return;
-        cudaEventRecord(ev.b, c->st);
+        cudaEventRecord(ev.b, s);
         c->prof_pending.push_back(ev);
     }
 };
@@ -783,20 +793,26 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
     return MSM_OK;
 }
 
-// d-dimensional transform (forward x,y,z / inverse z,y,x) with the operators of `o`
-int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2* src, int src_by_sid, double2* work,
-                  int work_by_sid, const XformOps& o) {
+// passes of a d-dimensional transform (forward x,y,z / inverse z,y,x) with the operators of `o`
+std::vector<PassSpec> transform_seq(const msm_ctx* ctx, bool inv, const XformOps& o) {
     std::vector<PassSpec> seq;
     for (int k = 0; k < ctx->dims; ++k) {
         const bool first = (k == 0), last = (k == ctx->dims - 1);
-        PassSpec s;
+        PassSpec s{};
         s.axis = inv ? ctx->dims - 1 - k : k;
         s.inv = inv;
         s.lop = (first && o.lop_first != L_NONE) ? o.lop_first : o.lop_each;
         s.sop = last ? o.sop_last : o.sop_each;
+        s.target = TG_MAIN;
+        s.tile0 = 0;
+        s.tile_end = -1;
         seq.push_back(s);
     }
-    return run_passes(ctx, seq, ids, ns, src, src_by_sid, work, work_by_sid, o);
+    return seq;
+}
+int run_transform(msm_ctx* ctx, bool inv, const int* ids, int ns, const double2* src, int src_by_sid, double2* work,
+                  int work_by_sid, const XformOps& o) {
+    return run_passes(ctx, transform_seq(ctx, inv, o), ids, ns, src, src_by_sid, work, work_by_sid, o);
 }
 
 int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 16); }
@@ -882,6 +898,46 @@ int allreduce_rho(msm_ctx* ctx, int plane) {
 int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, int ns, const double2* src, int src_by_sid,
                double2* work, int work_by_sid, const XformOps& o);
 
+// rows [k, k+1) * rows / ar_slabs of `plane` are final on the compute stream: sum them over the ranks on the
+// communication stream, behind the kernels that still compute the later ranges
+int allreduce_slab(msm_ctx* ctx, int plane, int k) {
+    const long long rows = ctx->C / ctx->n;
+    const long long r0 = rows * k / ctx->ar_slabs, r1 = rows * (k + 1) / ctx->ar_slabs;
+    double* r = reinterpret_cast<double*>(real_plane(ctx, plane)) + r0 * ctx->n;
+    if (cudaEventRecord(ctx->ev_slab[k], ctx->st) != cudaSuccess || cudaStreamWaitEvent(ctx->comm_st, ctx->ev_slab[k], 0) != cudaSuccess)
+        return fail(ctx, MSM_E_CUDA, "allreduce_slab: event handshake failed");
+    int rc;
+    {
+        ProfScope ps(ctx, "nccl_allreduce_rho", 0.0, ctx->comm_st);
+        rc = g_nccl.AllReduce(r, r, (size_t)((r1 - r0) * ctx->n), NCCL_DOUBLE, NCCL_SUM, ctx->comm, ctx->comm_st);
+    }
+    if (rc != 0)
+        return fail(ctx, MSM_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    if (cudaEventRecord(ctx->ev_ar[k], ctx->comm_st) != cudaSuccess) return fail(ctx, MSM_E_CUDA, "allreduce_slab: event record failed");
+    return MSM_OK;
+}
+
+// the LAST pass that completes the summed density (seq.back(), an x pass with a rho store operator), launched range by
+// range with the all-reduce of every finished range started at once
+int run_passes_slabbed(msm_ctx* ctx, std::vector<PassSpec> seq, const int* ids, int ns, const double2* src, int src_by_sid,
+                       double2* work, int work_by_sid, const XformOps& o, int plane) {
+    PassSpec last = seq.back();
+    seq.pop_back();
+    int rc;
+    if (!seq.empty() && (rc = run_passes(ctx, seq, ids, ns, src, src_by_sid, work, work_by_sid, o))) return rc;
+    const long long rows = ctx->C / ctx->n;
+    for (int k = 0; k < ctx->ar_slabs; ++k) {
+        last.tile0 = (int)(rows * k / ctx->ar_slabs / ctx->TX);
+        last.tile_end = (int)(rows * (k + 1) / ctx->ar_slabs / ctx->TX);
+        // (after the first pass of `seq` every pass reads the work array)
+        if ((rc = run_passes(ctx, std::vector<PassSpec>{last}, ids, ns, seq.empty() ? src : work, seq.empty() ? src_by_sid : work_by_sid,
+                             work, work_by_sid, o)))
+            return rc;
+        if ((rc = allreduce_slab(ctx, plane, k))) return rc;
+    }
+    return MSM_OK;
+}
+
 // Real-field Poisson solve (summed-density mode, dims == 3), in place on one real plane of n^3 doubles:
 //   phi = F^-1[ c / (k^2 n^3) F[rho] ]          (simulation_object.rs:1066-1110; the reference transforms the real
 //                                                density as a full complex array, :1071, :1105)
@@ -890,7 +946,7 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
 // n-point passes over the half-spectrum grid (last forward + multiplier + first inverse fused: S_POISSON_INV), the
 // Nyquist plane as a 2-D grid at fixed k_x; C2R: L_C2R + an n/2-point inverse pass puts phi back as the real plane.
 // Half the bytes and flops of the complex solve: 5 x 16 = 80 B per cell instead of 160 (+ 48 of pack / unpack).
-int poisson_real(msm_ctx* ctx, int plane, bool max_only, unsigned long long* maxbits) {
+int poisson_real(msm_ctx* ctx, int plane, bool max_only, unsigned long long* maxbits, bool slabbed = false) {
     const int id0 = 0;
     XformOps o;
     o.gsz = 1;
@@ -911,6 +967,18 @@ int poisson_real(msm_ctx* ctx, int plane, bool max_only, unsigned long long* max
     }
     fwd.push_back(PassSpec{1, true, L_NONE, S_NONE, TG_HALF_YZ});
     nyq.push_back(PassSpec{0, true, L_NONE, S_NONE, TG_NYQ});
+    if (slabbed) {
+        // the density arrives range by range from the all-reduce stream (allreduce_slab): R2C follows it
+        const long long rows = ctx->C / ctx->n;
+        for (int k = 0; k < ctx->ar_slabs; ++k) {
+            if (cudaStreamWaitEvent(ctx->st, ctx->ev_ar[k], 0) != cudaSuccess) return fail(ctx, MSM_E_CUDA, "cudaStreamWaitEvent failed");
+            PassSpec ps = fwd[0];
+            ps.tile0 = (int)(rows * k / ctx->ar_slabs / ctx->TXH);
+            ps.tile_end = (int)(rows * (k + 1) / ctx->ar_slabs / ctx->TXH);
+            if ((rc = run_passes(ctx, std::vector<PassSpec>{ps}, &id0, 1, r, 0, r, 0, o))) return rc;
+        }
+        fwd.erase(fwd.begin());
+    }
     if ((rc = run_passes(ctx, fwd, &id0, 1, r, 0, r, 0, o))) return rc;
     if ((rc = run_passes(ctx, nyq, &id0, 1, ctx->nyq, 0, ctx->nyq, 0, o))) return rc;
     std::vector<PassSpec> back{PassSpec{0, true, L_C2R, max_only ? S_MAX : S_NONE, TG_HALF_X}};
@@ -1207,7 +1275,8 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
             CUC(cudaStreamSynchronize(ctx->st));
         }
     }
-    if (cfg->coupling == MSM_COUPLING_SUMMED && cfg->nranks > 1) {
+    // the communicator: required by the summed-density mode, optional otherwise (msm_ensemble_allreduce)
+    if (cfg->nranks > 1 && (cfg->coupling == MSM_COUPLING_SUMMED || cfg->nccl_unique_id)) {
         if (!cfg->nccl_unique_id) return bail(MSM_E_ARG, "nranks > 1 requires nccl_unique_id");
         if (!g_nccl.load()) return bail(MSM_E_NCCL, "cannot load libnccl.so.2");
         nccl_uid_t id;
@@ -1217,6 +1286,23 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
             return bail(MSM_E_NCCL, std::string("ncclCommInitRank failed: ") +
                                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?") + " (code " +
                                         std::to_string(rc) + ")");
+        if (ctx->real_solve) {
+            // default 1 = one all-reduce after the last x pass: with 4 slabs the NCCL kernels compete with the pass they
+            // hide behind and the step got SLOWER at N = 2 (249.6 -> 259.8 ms, profiles/README.md); MSM_B200_AR_SLABS=4 for A/B
+            ctx->ar_slabs = 1;
+            if (const char* e = getenv("MSM_B200_AR_SLABS")) ctx->ar_slabs = std::max(1, std::min(8, atoi(e)));
+            // a slab must be whole tiles of both x-pass kernels and whole CTAs: rows per slab multiple of 64
+            while (ctx->ar_slabs > 1 && (((long long)n * n) % (64LL * ctx->ar_slabs))) ctx->ar_slabs /= 2;
+            if (ctx->ar_slabs > 1) {
+                int lo = 0, hi = 0;
+                CUC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CUC(cudaStreamCreateWithPriority(&ctx->comm_st, cudaStreamNonBlocking, hi));
+                for (int i = 0; i < ctx->ar_slabs; ++i) {
+                    CUC(cudaEventCreateWithFlags(&ctx->ev_slab[i], cudaEventDisableTiming));
+                    CUC(cudaEventCreateWithFlags(&ctx->ev_ar[i], cudaEventDisableTiming));
+                }
+            }
+        }
     }
 #undef CUC
     *out = ctx;
@@ -1243,6 +1329,7 @@ void msm_destroy(msm_ctx* ctx) {
     cudaFree(ctx->alias_out);
     cudaFree(ctx->maxbits);
     cudaFree(ctx->scratch_small);
+    cudaFree(ctx->ic_base);
     cudaFree(ctx->ens_psi);
     cudaFree(ctx->ens_psik);
     cudaFree(ctx->ens_psi2);
@@ -1271,6 +1358,14 @@ void msm_destroy(msm_ctx* ctx) {
     }
     for (cudaEvent_t e : ctx->tk_ev)
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 8; ++i) {
+        if (ctx->ev_slab[i]) cudaEventDestroy(ctx->ev_slab[i]);
+        if (ctx->ev_ar[i]) cudaEventDestroy(ctx->ev_ar[i]);
+    }
+    if (ctx->comm_st) {
+        cudaStreamSynchronize(ctx->comm_st);
+        cudaStreamDestroy(ctx->comm_st);
+    }
     if (ctx->tm_a) cudaEventDestroy(ctx->tm_a);
     if (ctx->tm_b) cudaEventDestroy(ctx->tm_b);
     if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -1752,7 +1847,8 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
 
     const int sg = ctx->cfg.n_streams_global > 0 ? ctx->cfg.n_streams_global : ctx->S;
     const bool real = summed && ctx->real_solve;
-    auto drift_inverse = [&](const int* cid, int ns, bool accumulate) {
+    const bool slabbed = real && ctx->cfg.nranks > 1 && ctx->ar_slabs > 1;   // all-reduce pipelined behind the last x pass
+    auto drift_inverse = [&](const int* cid, int ns, bool accumulate, bool completes_rho = false) {
         XformOps o;   // psi_k * drift -> psi (in place), rho out
         o.lop_each = L_DRIFT;
         o.sop_last = S_RHO_KEEP;
@@ -1762,6 +1858,8 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
         if (real) o.pbuf = real_plane(ctx, 0);
         o.rho_accumulate = accumulate ? 1 : 0;
         o.dtab_shared = summed && same_drift;
+        if (slabbed && completes_rho)
+            return run_passes_slabbed(ctx, transform_seq(ctx, true, o), cid, ns, ctx->X, 1, ctx->X, 1, o, 0);
         return run_transform(ctx, true, cid, ns, ctx->X, 1, ctx->X, 1, o);
     };
     auto kick_forward = [&](const int* cid, int ns, bool start_next_potential) {
@@ -1830,13 +1928,13 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
         // (first inverse pass into the scratch slots); its density accumulates into plane 1, which is reduced and solved
         // for max|phi| only.  Per step and rank: 2 x 8 B/cell over NVLink and 2 x 80 B/cell of replicated solve.
         const int d = ctx->dims;
-        const bool eager = ctx->fuse;
+        const bool eager = ctx->fuse, all_streams = ids.size() == (size_t)ctx->S;
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
-            if ((rc = drift_inverse(&ids[i], ns, i > 0))) return rc;
+            if ((rc = drift_inverse(&ids[i], ns, i > 0, i + ctx->chunk >= ids.size()))) return rc;
         }
-        if ((rc = allreduce_rho(ctx, 0))) return rc;
-        if ((rc = poisson_real(ctx, 0, false, nullptr))) return rc;
+        if (!slabbed && (rc = allreduce_rho(ctx, 0))) return rc;
+        if ((rc = poisson_real(ctx, 0, false, nullptr, slabbed))) return rc;
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
             if ((rc = kick_forward(&ids[i], ns, eager))) return rc;
@@ -1850,12 +1948,17 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
                 std::vector<PassSpec> seq;
                 for (int a = d - 2; a >= 1; --a) seq.push_back(PassSpec{a, true, L_NONE, S_NONE});
                 seq.push_back(PassSpec{0, true, L_NONE, S_RHO_ONLY});
-                if ((rc = run_passes(ctx, seq, &ids[i], ns, ctx->Tscr, 0, ctx->Tscr, 0, o))) return rc;
+                const bool completes = all_streams && slabbed && i + ctx->chunk >= ids.size();
+                rc = completes ? run_passes_slabbed(ctx, seq, &ids[i], ns, ctx->Tscr, 0, ctx->Tscr, 0, o, 1)
+                               : run_passes(ctx, seq, &ids[i], ns, ctx->Tscr, 0, ctx->Tscr, 0, o);
+                if (rc) return rc;
             }
         }
-        if (eager && ids.size() == (size_t)ctx->S) {   // the shared potential needs every stream's density
+        if (eager && all_streams) {   // the shared potential needs every stream's density
             CU(cudaMemsetAsync(ctx->maxbits, 0, sizeof(unsigned long long) * (ctx->S + 2), ctx->st));
-            if ((rc = summed_potential(ctx, true, ctx->maxbits))) return rc;
+            if (slabbed) rc = poisson_real(ctx, 1, true, ctx->maxbits, true);
+            else rc = summed_potential(ctx, true, ctx->maxbits);
+            if (rc) return rc;
             ctx->pmax_pending = ids;
         }
     } else {
@@ -2086,6 +2189,36 @@ int msm_ic_copy(msm_ctx* ctx, int32_t dst, int32_t src) {
     return MSM_OK;
 }
 
+int msm_ic_store(msm_ctx* ctx, int32_t s) {
+    if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_store: bad argument");
+    if (!ctx->has_psi[s]) return fail(ctx, MSM_E_STATE, "msm_ic_store: stream is empty");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
+    const size_t cb = sizeof(double2) * (size_t)ctx->C;
+    if (!ctx->ic_base) {
+        if (cudaMalloc(&ctx->ic_base, cb) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, MSM_E_NOMEM, "msm_ic_store: no memory for the saved wavefunction");
+        }
+        ctx->bytes += cb;
+    }
+    CU(cudaMemcpyAsync(ctx->ic_base, ctx->X + (size_t)s * ctx->C, cb, cudaMemcpyDeviceToDevice, ctx->st));
+    ctx->ic_base_in_k = ctx->in_k[s];
+    return MSM_OK;
+}
+
+int msm_ic_load(msm_ctx* ctx, int32_t s) {
+    if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_ic_load: bad argument");
+    if (!ctx->ic_base) return fail(ctx, MSM_E_STATE, "msm_ic_load: nothing stored (call msm_ic_store first)");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (int rc = wait_upload(ctx, s)) return rc;
+    CU(cudaMemcpyAsync(ctx->X + (size_t)s * ctx->C, ctx->ic_base, sizeof(double2) * (size_t)ctx->C, cudaMemcpyDeviceToDevice, ctx->st));
+    ctx->in_k[s] = ctx->ic_base_in_k;
+    ctx->has_psi[s] = 1;
+    invalidate_stream(ctx, s);
+    return MSM_OK;
+}
+
 int msm_sample_perturbation(msm_ctx* ctx, int32_t s, int32_t scheme, uint64_t seed, double n_tot) {
     if (!ctx || s < 0 || s >= ctx->S) return fail(ctx, MSM_E_ARG, "msm_sample_perturbation: bad argument");
     if (!ctx->has_psi[s] || ctx->in_k[s]) return fail(ctx, MSM_E_STATE, "msm_sample_perturbation: psi must be freshly set");
@@ -2159,6 +2292,27 @@ int msm_ensemble_accumulate(msm_ctx* ctx, const int32_t* active) {
         }
         ctx->launches++;
         CU(cudaGetLastError());
+    }
+    return MSM_OK;
+}
+
+int msm_ensemble_allreduce(msm_ctx* ctx) {
+    if (!ctx) return MSM_E_ARG;
+    if (!ctx->ens_psi) return fail(ctx, MSM_E_STATE, "msm_ensemble_allreduce: call msm_ensemble_accumulate first");
+    if (ctx->cfg.nranks <= 1) return MSM_OK;
+    if (!ctx->comm) return fail(ctx, MSM_E_STATE, "msm_ensemble_allreduce: the context was created without nccl_unique_id");
+    CU(cudaSetDevice(ctx->cfg.device));
+    // the four accumulators of synthesizer/src/lib.rs:217-240, summed over the ranks in place (complex grids as 2 C doubles)
+    struct { void* p; size_t n; } grids[4] = {{ctx->ens_psi, 2 * (size_t)ctx->C}, {ctx->ens_psik, 2 * (size_t)ctx->C},
+                                              {ctx->ens_psi2, (size_t)ctx->C}, {ctx->ens_psik2, (size_t)ctx->C}};
+    for (auto& g : grids) {
+        int rc;
+        {
+            ProfScope ps(ctx, "nccl_allreduce_ensemble", 0.0);
+            rc = g_nccl.AllReduce(g.p, g.p, g.n, NCCL_DOUBLE, NCCL_SUM, ctx->comm, ctx->st);
+        }
+        if (rc != 0)
+            return fail(ctx, MSM_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     }
     return MSM_OK;
 }

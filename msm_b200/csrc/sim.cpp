@@ -598,9 +598,38 @@ int msm_sim_update_streams(msm_sim* sim, const int32_t* subset) {
 // of up to chunk_streams, and while group c computes, the ICs of group c+1 cross PCIe on the upload stream and the final
 // wavefunctions of group c-1 leave on the copy stream (one download enqueued after every update, so that the two
 // staging buffers never stall the step kernels).
+// `prepare(i)` puts the initial wavefunction of streams[i] in place (returns 0 / an error code; < 0 on error, 1 = the
+// stream keeps its current state): an asynchronous upload from host memory, or a device-side build from a seed.
+static int run_streams_impl(msm_sim* sim, int32_t n, const int32_t* streams, const std::function<int(int)>& prepare,
+                            double* const* re_out, double* const* im_out, uint64_t max_updates);
+
 int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const double* const* psi_in, double* const* re_out,
                         double* const* im_out, uint64_t max_updates) {
     if (!sim || n < 0 || (n > 0 && !streams)) return sfail(sim, MSM_E_ARG, "msm_sim_run_streams: bad argument");
+    auto prepare = [&](int i) -> int {
+        if (!psi_in || !psi_in[i]) return 1;
+        return msm_upload_begin(sim->ctx, streams[i], psi_in[i]);
+    };
+    return run_streams_impl(sim, n, streams, prepare, re_out, im_out, max_updates);
+}
+
+int msm_sim_run_streams_seeded(msm_sim* sim, int32_t n, const int32_t* streams, int32_t scheme, const uint64_t* seeds,
+                               double* const* re_out, double* const* im_out, uint64_t max_updates) {
+    if (!sim || n < 0 || (n > 0 && (!streams || !seeds))) return sfail(sim, MSM_E_ARG, "msm_sim_run_streams_seeded: bad argument");
+    // new_from_params (simulation_object.rs:404-435): the un-sampled initial condition (saved once by msm_ic_store), then
+    // sample_quantum_perturbation with the stream's seed (ics.rs:434-648) -- both on the device, enqueued behind the
+    // kernels of the previous group; only scalars cross PCIe on the way in.
+    auto prepare = [&](int i) -> int {
+        int rc = msm_ic_load(sim->ctx, streams[i]);
+        if (rc == MSM_OK && seeds[i] != MSM_SEED_NONE)
+            rc = msm_sample_perturbation(sim->ctx, streams[i], scheme, seeds[i], sim->d.n_tot);
+        return rc;
+    };
+    return run_streams_impl(sim, n, streams, prepare, re_out, im_out, max_updates);
+}
+
+static int run_streams_impl(msm_sim* sim, int32_t n, const int32_t* streams, const std::function<int(int)>& prepare,
+                            double* const* re_out, double* const* im_out, uint64_t max_updates) {
     const msm_sim_params& p = sim->p;
     const int S = p.n_streams;
     if (p.coupling == MSM_COUPLING_SUMMED)
@@ -624,13 +653,14 @@ int msm_sim_run_streams(msm_sim* sim, int32_t n, const int32_t* streams, const d
     };
     auto upload_group = [&](int c) -> int {
         for (int i = bounds[c]; i < bounds[c + 1]; ++i) {
-            if (!psi_in || !psi_in[i]) continue;
+            const int rc = prepare(i);
+            if (rc < 0) return rc;
+            if (rc == 1) continue;                                               // keeps its current state
             Stream fresh;                                                        // a new SimulationObject (:404-449)
             fresh.time = p.time;
             fresh.tau = sim->d.tau0;
             if (p.expanding) fresh.solver = ScaleFactorSolver(sim->cosmo);
             sim->st[streams[i]] = fresh;
-            if (int rc = msm_upload_begin(sim->ctx, streams[i], psi_in[i])) return rc;
         }
         return MSM_OK;
     };

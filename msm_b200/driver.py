@@ -150,11 +150,12 @@ def main(argv=None) -> int:
     return 0
 
 
-def combine_streams(sim: SimulationObject, n_streams_global: int, dx: float, active=None) -> dict:
+def combine_streams(sim: SimulationObject, n_streams_global: int, dx: float, active=None, allreduce: bool = False) -> dict:
     """The synthesizer's per-dump products from the resident wavefunctions (synthesizer/src/lib.rs:106-342,
     main.rs:63-93,161-173): means over streams of psi, |psi|^2, psi_k, |psi_k|^2 and Qx = sum(<|psi|^2> - |<psi>|^2) dV.
-    With several ranks, sum the four arrays over ranks before dividing (they are plain sums)."""
-    sums = sim.grid.ensemble_sums(active)
+    With several ranks (a context created with an nccl_unique_id), allreduce=True sums the four accumulators over the
+    ranks on the device before the division, so every rank holds the ensemble means of ALL streams."""
+    sums = sim.grid.ensemble_sums(active, allreduce=allreduce)
     means = {k: v / float(n_streams_global) for k, v in sums.items()}
     dv = dx ** sim.parameters.dims
     means["Qx"] = complex(np.sum(means["psi2"] - means["psi"] * np.conj(means["psi"])) * dv)

@@ -56,4 +56,34 @@ for name, per_rank, size in (("spherical-tophat", 3, None), ("spherical-tophat-c
     if int(t.item()) != 0:
         dist.destroy_process_group()
         sys.exit(1)
+
+# ensemble statistics over ALL streams: per-rank accumulation + ncclAllReduce of the four grids inside
+# the library, against the restatement of the synthesizer (synthesizer/src/lib.rs:106-342) on the host
+from msm_b200 import driver
+per_rank = 2
+S = per_rank * world
+ps = gu.oracle_streams("spherical-tophat", limit=S)
+psi0s = [gu.initial_wavefunction(p) for p in ps]
+sim = m.SimulationObject(gu.to_msm_params(ps[0]), n_streams=per_rank, device=local, rank=rank, nranks=world,
+                         n_streams_global=S, nccl_unique_id=fresh_unique_id())       # independent streams + a communicator
+refs = []
+for li in range(per_rank):
+    sim.set_psi(li, psi0s[rank * per_rank + li])
+for s in range(S):
+    refs.append(o.SimulationObject(ps[s], psi0s[s]))
+for _ in range(3):
+    sim.update()
+    for r in refs:
+        r.update()
+got = driver.combine_streams(sim, S, ps[0].dx, allreduce=True)
+want = o.synthesizer_combine([r.psi for r in refs], ps[0].dx ** 3)
+worst = max(np.linalg.norm((got[k] - want[k]).ravel()) / np.linalg.norm(np.asarray(want[k]).ravel()) for k in ("psi", "psi2", "psik", "psik2"))
+norm = float(np.sum(want["psi2"]).real) * ps[0].dx ** 3          # Qx is a difference of O(norm) sums: absolute bound
+ok = worst < 1e-10 and abs(got["Qx"] - want["Qx"]) <= 1e-12 * norm
+print(f"rank {rank} ensemble over {S} streams on {world} ranks: worst rel-L2 {worst:.2e}, Qx {got['Qx'].real:.6e} vs {want['Qx'].real:.6e} -> {'OK' if ok else 'FAIL'}", flush=True)
+sim.close()
+t = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+dist.all_reduce(t)
+code = int(t.item())
 dist.destroy_process_group()
+sys.exit(1 if code else 0)

@@ -348,6 +348,30 @@ def test_run_streams_matches_oracle_and_the_sequential_path(monkeypatch, nstream
     sim.close()
 
 
+def test_run_streams_seeded_builds_the_initial_conditions_on_the_device():
+    """msm_sim_run_streams_seeded: un-sampled IC saved once on the device + the seeded sampler per stream (the reference's
+    `new_from_params`, simulation_object.rs:404-435), then the same pipelined loop; against the oracle run of every stream
+    of examples/spherical-tophat.toml (Husimi seeds + the trailing un-sampled mean-field run)."""
+    ps = oracle_streams("spherical-tophat")
+    ps = ps[:5] + [ps[-1]]
+    assert ps[-1].sampling_parameters is None
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=len(ps), chunk_streams=2)
+    ics = ps[0].ics
+    sim.grid.ic_spherical_tophat(0, ps[0].axis_length, float(ics["radius"]), float(ics["delta"]), float(ics["slope"]))
+    sim.grid.ic_store(0)
+    seeds = [p.sampling_parameters["seed"] if p.sampling_parameters else None for p in ps]
+    re = [np.empty((16,) * 3) for _ in ps]
+    im = [np.empty((16,) * 3) for _ in ps]
+    sim.run_streams_seeded(list(range(len(ps))), "Husimi", seeds, re, im, max_updates=4)
+    for i, p in enumerate(ps):
+        ref = o.SimulationObject(p, initial_wavefunction(p))
+        for _ in range(4):
+            ref.update()
+        assert sim.state(i).n_steps == 4 and abs(sim.state(i).time - ref.parameters.time) <= 1e-13 * ref.parameters.time
+        assert rel_l2(re[i] + 1j * im[i], ref.psi) < 1e-10, i
+    sim.close()
+
+
 def test_async_transfers_order_against_compute():
     """msm_upload_begin / msm_download_begin: uploads land before the compute stream touches the stream, downloads
     see everything enqueued before them."""
