@@ -108,13 +108,19 @@ extern "C" {
     pub fn msm_sim_state(sim: *const MsmSim, stream: i32, out: *mut MsmStreamState) -> c_int;
     pub fn msm_sim_get_psi(sim: *mut MsmSim, stream: i32, re: *mut f64, im: *mut f64) -> c_int;
     pub fn msm_sim_dump(sim: *mut MsmSim, stream: i32, root: *const c_char, name: *const c_char, idx: u32) -> c_int;
+    pub fn msm_sim_dump_potential(sim: *mut MsmSim, stream: i32, root: *const c_char, name: *const c_char, idx: u32) -> c_int;
     pub fn msm_sim_wait_io(sim: *mut MsmSim) -> c_int;
+    pub fn msm_sim_run_streams_seeded(sim: *mut MsmSim, n: i32, streams: *const i32, scheme: i32, seeds: *const u64,
+                                      re_out: *const *mut f64, im_out: *const *mut f64, max_updates: u64) -> c_int;
     // grid level, for hosts that keep get_timestep / the scale-factor solver in Rust
     pub fn msm_potential_max(ctx: *mut MsmCtx, active: *const i32, max_abs_phi: *mut f64) -> c_int;
     pub fn msm_step(ctx: *mut MsmCtx, active: *const i32, drift: *const f64, kick: *const f64, alias: *mut f64) -> c_int;
     pub fn msm_get_potential(ctx: *mut MsmCtx, stream: i32, phi: *mut f64) -> c_int;
     pub fn msm_ensemble_accumulate(ctx: *mut MsmCtx, active: *const i32) -> c_int;
+    pub fn msm_ensemble_allreduce(ctx: *mut MsmCtx) -> c_int;
     pub fn msm_ensemble_get(ctx: *mut MsmCtx, field: i32, re: *mut f64, im: *mut f64) -> c_int;
+    pub fn msm_ic_store(ctx: *mut MsmCtx, stream: i32) -> c_int;
+    pub fn msm_ic_load(ctx: *mut MsmCtx, stream: i32) -> c_int;
 }
 
 #[derive(Debug)]

@@ -148,7 +148,9 @@ template <int N, bool XL, int EV = Plan<N>::E> constexpr int tile_threads() { re
 #endif
 template <int N, bool XL, int EV = Plan<N>::E> constexpr int tile_minb() {
     if (EV != Plan<N>::E) return Plan<N>::MINB;   // wide variant: half the threads, the same CTAs, twice the registers
-    return (XL && tile_T<N, XL>() != Plan<N>::T) ? MSM_XL_MINB : Plan<N>::MINB * (Plan<N>::T / tile_T<N, XL>());
+    // (a 256-point line has 32 threads, so a T = 2 tile is a 64-thread CTA: twice the CTAs for the same 16 resident warps
+    //  at 128 registers -- ncu showed the n/2 = 256-point R2C / C2R kernels of the 512^3 real-field solve at 8 warps / SM)
+    return (XL && tile_T<N, XL>() != Plan<N>::T) ? MSM_XL_MINB * (N == 256 ? 2 : 1) : Plan<N>::MINB * (Plan<N>::T / tile_T<N, XL>());
 }
 // Points per thread of one kernel instance.  E = 8 everywhere (Plan) except where a kernel measured faster with E = 16
 // (half the threads, 128 registers, the same two CTAs per SM): the two-transform strided kernel `drift+alias+inv`, which
@@ -472,7 +474,7 @@ constexpr bool uses_dtab(int lop, int sop) { return lop == L_DRIFT || sop == S_D
 #endif
 template <int N, int LOP, int SOP, bool XL> constexpr int kernel_minb() {
     constexpr int EV = plan_E<N, LOP, SOP, XL>();
-    if (EV == Plan<N>::E && XL && tile_T<N, XL>() != Plan<N>::T && !uses_dtab(LOP, SOP)) return MSM_XL_MINB_NODT;
+    if (EV == Plan<N>::E && XL && tile_T<N, XL>() != Plan<N>::T && !uses_dtab(LOP, SOP)) return MSM_XL_MINB_NODT * (N == 256 ? 2 : 1);
     return tile_minb<N, XL, EV>();
 }
 template <int N, int LOP, int SOP> constexpr int table_elems() {   // double2 units

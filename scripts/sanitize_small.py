@@ -40,6 +40,8 @@ run("spherical-tophat-cosmo", None, 2, 2)
 run("spherical-tophat", 32, 2, 2, dims=2)
 run("repro-planeWave1d", None, 2, 2)
 run("spherical-tophat", None, 3, 2, coupling=m.COUPLING_SUMMED, chunk=2)
+run("spherical-tophat", 32, 3, 2, coupling=m.COUPLING_SUMMED, chunk=2)     # real-field solve: n/2 = 16 point R2C / C2R
+run("spherical-tophat", 64, 2, 1, coupling=m.COUPLING_SUMMED)
 run("spherical-tophat", 64, 2, 1)
 run("spherical-tophat", 128, 2, 1)
 os.environ["MSM_B200_LB"] = "2"
