@@ -360,14 +360,14 @@ def main():
     ach = top["algorithmic_bytes"] / (top["ms_total"] * 1e-3) / 1e9
     kernel_ms = sum(r["ms_total"] for r in prof)
     # DRAM traffic of that kernel per launch, from the committed `ncu --set full` capture of the same launch shape
-    # (profiles/r01g_ncu_dram_traffic.json: 8 streams per launch, 512^3); null when the shape differs
+    # (profiles/r02g_ncu_dram_traffic.json: 8 streams per launch, 512^3); null when the shape differs
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01g_ncu_dram_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02g_ncu_dram_traffic.json")
     if os.path.exists(tpath) and size == 512 and chunk == 8 and n_local >= 8:
         key = top["name"][:-3] + (",x>" if top["name"].endswith(",x>") else ",yz>")
         for k, v in json.load(open(tpath)).items():
             if k.startswith(key):
-                traffic, traffic_src = v["dram_bytes_per_launch"], "profiles/r01g_ncu_dram_traffic.json"
+                traffic, traffic_src = v["dram_bytes_per_launch"], "profiles/r02g_ncu_dram_traffic.json"
     roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "traffic_measured_in_run": False,
                 "algorithmic_bytes_per_launch": top["algorithmic_bytes"] / top["launches"], "peak_source": peak_src,

@@ -1287,9 +1287,10 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
                                         (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?") + " (code " +
                                         std::to_string(rc) + ")");
         if (ctx->real_solve) {
-            // default 1 = one all-reduce after the last x pass: with 4 slabs the NCCL kernels compete with the pass they
-            // hide behind and the step got SLOWER at N = 2 (249.6 -> 259.8 ms, profiles/README.md); MSM_B200_AR_SLABS=4 for A/B
-            ctx->ar_slabs = 1;
+            // measured (profiles/README.md): 4 slabs are FASTER where NCCL reduces in the switch (NVLS; N = 4: 134.5 -> 132.9 ms,
+            // N = 8: 71.6 -> 69.7 ms per step) and SLOWER on 2 ranks (ring over P2P: 249.6 -> 259.8 ms, the NCCL kernels compete
+            // with the pass they hide behind).  MSM_B200_AR_SLABS overrides.
+            ctx->ar_slabs = cfg->nranks >= 4 ? 4 : 1;
             if (const char* e = getenv("MSM_B200_AR_SLABS")) ctx->ar_slabs = std::max(1, std::min(8, atoi(e)));
             // a slab must be whole tiles of both x-pass kernels and whole CTAs: rows per slab multiple of 64
             while (ctx->ar_slabs > 1 && (((long long)n * n) % (64LL * ctx->ar_slabs))) ctx->ar_slabs /= 2;
