@@ -1929,7 +1929,8 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
         // (first inverse pass into the scratch slots); its density accumulates into plane 1, which is reduced and solved
         // for max|phi| only.  Per step and rank: 2 x 8 B/cell over NVLink and 2 x 80 B/cell of replicated solve.
         const int d = ctx->dims;
-        const bool eager = ctx->fuse, all_streams = ids.size() == (size_t)ctx->S;
+        const bool all_streams = ids.size() == (size_t)ctx->S;
+        const bool eager = ctx->fuse && all_streams;   // the shared potential needs every stream's density
         for (size_t i = 0; i < ids.size(); i += ctx->chunk) {
             const int ns = (int)std::min<size_t>(ctx->chunk, ids.size() - i);
             if ((rc = drift_inverse(&ids[i], ns, i > 0, i + ctx->chunk >= ids.size()))) return rc;
@@ -1955,7 +1956,7 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
                 if (rc) return rc;
             }
         }
-        if (eager && all_streams) {   // the shared potential needs every stream's density
+        if (eager) {
             CU(cudaMemsetAsync(ctx->maxbits, 0, sizeof(unsigned long long) * (ctx->S + 2), ctx->st));
             if (slabbed) rc = poisson_real(ctx, 1, true, ctx->maxbits, true);
             else rc = summed_potential(ctx, true, ctx->maxbits);

@@ -213,9 +213,38 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 static __device__ __noinline__ void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }
 
-// sin and cos of the kick phase -kappa*phi.  |x| <= 1e5: three-term Cody-Waite reduction by pi/2 (exact products via
-// FMA) + the fdlibm minimax kernels on [-pi/4, pi/4] (< 1 ulp); larger arguments take the library path.
+// sin and cos of the kick phase -kappa*phi: the fdlibm minimax kernels on [-pi/4, pi/4] (< 1 ulp).
+//   |x| <= pi/4   no reduction, no quadrant logic.  This is the path the integrator takes: dt <= cfl * pi * hbar / max|phi|
+//                 (simulation_object.rs:906-909) bounds the kick phase by cfl * pi of the dt-potential, so with cfl <= 0.25
+//                 practically every cell of every step lands here; the branch is taken per warp, a warp whose 32 phases are
+//                 all small never executes the rest (round 2: the reduction and the selects were 14 of the 40
+//                 instructions of every sincos).  Bit-identical to the general path, which gives q = 0, r = x here.
+//   |x| <= 1e5    three-term Cody-Waite reduction by pi/2 (exact products via FMA);  larger arguments: library path.
+__device__ __forceinline__ void sincos_kernels(double r, double* sn, double* cs) {
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    *sn = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    *cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+}
+#ifndef MSM_KICK_FASTPATH
+#define MSM_KICK_FASTPATH 1
+#endif
 __device__ __forceinline__ void kick_sincos(double x, double* s, double* c) {
+#if MSM_KICK_FASTPATH
+    if (fabs(x) <= 0.78539816339744828) {
+        sincos_kernels(x, s, c);
+        return;
+    }
+#endif
     if (fabs(x) > 1.0e5) {
         sincos_slow(x, s, c);
         return;
@@ -225,19 +254,8 @@ __device__ __forceinline__ void kick_sincos(double x, double* s, double* c) {
     r = fma(-q, 6.123233995736766e-17, r);
     r = fma(-q, -1.4973849048591698e-33, r);
     const int n = (int)q;
-    const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    const double sn = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+    double sn, cs;
+    sincos_kernels(r, &sn, &cs);
     const double a = (n & 1) ? cs : sn, b = (n & 1) ? sn : cs;
     *s = (n & 2) ? -a : a;
     *c = ((n + 1) & 2) ? -b : b;
