@@ -29,14 +29,22 @@ def fresh_unique_id():
     return bytes(uid.cpu().numpy().tobytes())
 
 
-for name, per_rank, size in (("spherical-tophat", 3, None), ("spherical-tophat-cosmo", 2, None), ("spherical-tophat", 2, 64)):
+# (name, streams per rank, grid size, chunk_streams, MSM_B200_AR_SLABS): the last two cases force the slab-pipelined
+# all-reduce (the default for >= 4 ranks), once with several chunks of local streams accumulating into the same plane
+for name, per_rank, size, chunk, slabs in (("spherical-tophat", 3, None, 0, None), ("spherical-tophat-cosmo", 2, None, 0, None),
+                                           ("spherical-tophat", 2, 64, 0, None), ("spherical-tophat", 3, 32, 2, "4"),
+                                           ("spherical-tophat-cosmo", 2, None, 0, "2")):
+    if slabs is None:
+        os.environ.pop("MSM_B200_AR_SLABS", None)
+    else:
+        os.environ["MSM_B200_AR_SLABS"] = slabs
     S = per_rank * world
     ps = gu.oracle_streams(name, size, limit=S)
     psi0s = [gu.initial_wavefunction(p) for p in ps]
     ens = o.SummedEnsemble(ps[0], psi0s)
     uid_bytes = fresh_unique_id()
     sim = m.SimulationObject(gu.to_msm_params(ps[0]), n_streams=per_rank, coupling=m.COUPLING_SUMMED, device=local,
-                             rank=rank, nranks=world, n_streams_global=S, nccl_unique_id=uid_bytes)
+                             chunk_streams=chunk, rank=rank, nranks=world, n_streams_global=S, nccl_unique_id=uid_bytes)
     mine = list(range(rank * per_rank, (rank + 1) * per_rank))
     for li, s in enumerate(mine):
         sim.set_psi(li, psi0s[s])
@@ -49,13 +57,14 @@ for name, per_rank, size in (("spherical-tophat", 3, None), ("spherical-tophat-c
         worst = max(worst, np.linalg.norm((got - ens.streams[s].psi).ravel()) / np.linalg.norm(ens.streams[s].psi.ravel()))
     st = sim.state(0)
     ok = worst < 1e-10 and abs(st.dt - ens.head.last_dt) <= 1e-12 * ens.head.last_dt
-    print(f"rank {rank} {name} size {size or 16} S={S}: psi rel-L2 {worst:.2e}, dt {st.dt:.6e} vs {ens.head.last_dt:.6e} -> {'OK' if ok else 'FAIL'}", flush=True)
+    print(f"rank {rank} {name} size {size or 16} S={S} chunk={chunk} slabs={slabs or 'default'}: psi rel-L2 {worst:.2e}, dt {st.dt:.6e} vs {ens.head.last_dt:.6e} -> {'OK' if ok else 'FAIL'}", flush=True)
     sim.close()
     t = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
     dist.all_reduce(t)
     if int(t.item()) != 0:
         dist.destroy_process_group()
         sys.exit(1)
+os.environ.pop("MSM_B200_AR_SLABS", None)
 
 # ensemble statistics over ALL streams: per-rank accumulation + ncclAllReduce of the four grids inside
 # the library, against the restatement of the synthesizer (synthesizer/src/lib.rs:106-342) on the host
