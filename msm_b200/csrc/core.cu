@@ -444,6 +444,7 @@ struct msm_ctx {
     std::vector<double> h_ksq;
     double four_pi2 = 0, k2_max = 0, dv = 0;
     int ntiles_last = 0, ntiles_used = 0;   // allocation pitch bound / tiles of the last forward pass as launched
+    int alias_count = 0;                    // alias partials per stream written by the last alias pass (MSM_ALIAS_PER_CTA: CTAs)
     uint64_t bytes = 0, launches = 0;
     void* comm = nullptr;
     cudaEvent_t tm_a = nullptr, tm_b = nullptr;
@@ -757,6 +758,8 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         p.tiles_per_cta = (int)std::__gcd((long long)(xl ? ctx->tiles_per_cta_x : ctx->tiles_per_cta), (long long)g.tiles_inner);
         if (p.tile0 % p.tiles_per_cta) p.tiles_per_cta = (int)std::__gcd((long long)p.tiles_per_cta, (long long)p.tile0);
         p.l2_prefetch = ctx->l2_prefetch;
+        if (sop_is_alias(sop))
+            ctx->alias_count = MSM_ALIAS_PER_CTA ? (g.ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta : g.ntiles;
         snprintf(nm, sizeof nm, "fft_pass<%d,%s,%s,%s,%s%s>", N, inv ? "inv" : "fwd", lop_name(lop), sop_name(sop),
                  axis == 0 ? "x" : axis == 1 ? "y" : "z", tg == TG_MAIN ? "" : tg == TG_NYQ ? ",nyquist" : ",half");
         const double frac = (double)(p.tile_end - p.tile0) / (double)g.ntiles;
@@ -1977,7 +1980,7 @@ int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift, const dou
     }
     {
         ProfScope ps(ctx, "alias_reduce", 8.0 * ctx->S * ctx->ntiles_last);
-        k_alias_reduce<<<ctx->S, 256, 0, ctx->st>>>(ctx->alias_partial, ctx->alias_out, ctx->ntiles_used, ctx->ntiles_used, ctx->dv);
+        k_alias_reduce<<<ctx->S, 256, 0, ctx->st>>>(ctx->alias_partial, ctx->alias_out, ctx->alias_count, ctx->ntiles_used, ctx->dv);
     }
     ctx->launches++;
     CU(cudaGetLastError());

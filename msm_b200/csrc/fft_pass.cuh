@@ -166,6 +166,11 @@ template <int N, bool XL, int EV = Plan<N>::E> constexpr int tile_minb() {
 #ifndef MSM_PI_NOSTASH
 #define MSM_PI_NOSTASH 1
 #endif
+// check_alias partial sums: 1 = one per (stream, CTA), reduced after the tile loop; 0 = one per (stream, tile) with a
+// CTA-wide barrier at the end of every item (round 1)
+#ifndef MSM_ALIAS_PER_CTA
+#define MSM_ALIAS_PER_CTA 1
+#endif
 template <int N, int LOP, int SOP, bool XL> constexpr int plan_E() {
     return (N == 512 && !XL && ((MSM_WIDE_DAI && SOP == 11 /* S_DRIFT_ALIAS_IZ */) || (MSM_WIDE_PI && SOP == 8 /* S_POISSON_INV */)))
                ? 16 : Plan<N>::E;
@@ -540,7 +545,9 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     }
     if constexpr (kTwSmem || sop_needs_k2(SOP) || uses_wreal(LOP, SOP)) __syncthreads();
     unsigned long long run_max = 0ull, run_max2 = 0ull;   // S_MAX with one buffer per CTA column: reduced once, after the tile loop
-    int item_parity = 0;
+    [[maybe_unused]] int item_parity = 0;
+    // check_alias partial sums of the (at most two) streams of this CTA's group, carried over all its tiles
+    [[maybe_unused]] double alias0 = 0.0, alias1 = 0.0;
 
     const int tid = threadIdx.x;
     const int l = XL ? tid / NT : tid % T;
@@ -949,6 +956,14 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
                 }
             }
         }
+#if MSM_ALIAS_PER_CTA
+        if constexpr (sop_is_alias(SOP)) {
+            // alias passes run in groups of at most two streams: a thread keeps one running sum per stream over all tiles
+            // of its CTA; the block reduction happens once, after the tile loop (no CTA-wide barrier per item)
+            if (q == 0) alias0 += acc;
+            else alias1 += acc;
+        }
+#else
         if constexpr (sop_is_alias(SOP)) {
             // one partial per (stream, tile), summed in a fixed order -> deterministic.  `red` is double buffered by
             // item parity: by the time a parity is reused the stage barriers of the item in between have passed.
@@ -962,6 +977,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             }
             item_parity ^= 1;
         }
+#endif
         if constexpr (SOP == S_MAX) {
             run_max = umax64(run_max, mx);
             run_max2 = umax64(run_max2, mx2);
@@ -985,6 +1001,22 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
 #endif
     }   // tiles of this CTA
 
+#if MSM_ALIAS_PER_CTA
+    if constexpr (sop_is_alias(SOP)) {
+        // one partial per (stream, CTA), every sum in a fixed order -> deterministic (simulation_object.rs:1259-1280)
+        const double a0 = warp_sum(alias0), a1 = warp_sum(alias1);
+        if ((tid & 31) == 0) {
+            red[0][tid >> 5] = a0;
+            red[1][tid >> 5] = a1;
+        }
+        __syncthreads();
+        if (tid < 2 && tid < p.gsz && g * p.gsz + tid < p.ns) {
+            double tot = 0.0;
+            for (int w = 0; w < (THREADS + 31) / 32; ++w) tot += red[tid][w];
+            p.alias_partial[(long long)p.sid[g * p.gsz + tid] * p.ntiles + blockIdx.x] = tot;
+        }
+    }
+#endif
     if constexpr (SOP == S_MAX) {
         if (p.gsz == 1 && g < p.ns) {
             // max|re|, max|im| of this CTA's tiles of buffer g; bit patterns of non-negative doubles order like integers

@@ -446,15 +446,16 @@ def test_summed_mode_matches_oracle(name, nstreams):
     sim.close()
 
 
-@pytest.mark.parametrize("size,nstreams,chunk,lb,real", [(32, 3, 2, 0, 1), (64, 2, 0, 0, 1), (64, 5, 4, 2, 1), (128, 2, 0, 3, 1),
-                                                         (32, 3, 2, 0, 0)])
-def test_summed_mode_real_field_solve(monkeypatch, size, nstreams, chunk, lb, real):
+@pytest.mark.parametrize("size,nstreams,chunk,lb,real,fuse", [(32, 3, 2, 0, 1, 1), (64, 2, 0, 0, 1, 1), (64, 5, 4, 2, 1, 1),
+                                                              (128, 2, 0, 3, 1, 1), (32, 3, 2, 0, 0, 1), (32, 3, 2, 0, 1, 0)])
+def test_summed_mode_real_field_solve(monkeypatch, size, nstreams, chunk, lb, real, fuse):
     """The shared potential of the summed-density mode is solved on the REAL density: n/2-point R2C / C2R passes along x,
     half-spectrum y / z passes, Nyquist plane (n/2 = 16 .. 64 here, 256 in test_gpu_headline.py), with the blocked
     device layout forced as well; real = 0 runs the complex fallback for comparison.  Trajectory, dt, max|phi| and the
     potential itself against the oracle ensemble."""
     monkeypatch.setenv("MSM_B200_LB", str(lb))
     monkeypatch.setenv("MSM_B200_REAL", str(real))
+    monkeypatch.setenv("MSM_B200_FUSE", str(fuse))               # 0: un-fused pass sequences, no eager dt-potential
     ps = oracle_streams("spherical-tophat", size, limit=nstreams)
     psi0s = [initial_wavefunction(p) for p in ps]
     ens = o.SummedEnsemble(ps[0], psi0s)
@@ -475,6 +476,26 @@ def test_summed_mode_real_field_solve(monkeypatch, size, nstreams, chunk, lb, re
     sim.update()                                     # the cached max|phi| survived the potential download
     ens.update()
     assert abs(sim.state(0).dt - ens.head.last_dt) <= 1e-13 * ens.head.last_dt
+    sim.close()
+
+
+@pytest.mark.parametrize("dims", [1, 2])
+def test_summed_mode_in_one_and_two_dimensions(dims):
+    """dims < 3 keep the complex Poisson solve (the real-field path needs the three-pass structure)"""
+    t = __import__("golden_util").load_toml("spherical-tophat", 32)
+    t.dims = dims
+    ps = list(o.simulation_iter(t))[:3]
+    psi0s = [initial_wavefunction(p) for p in ps]
+    ens = o.SummedEnsemble(ps[0], psi0s)
+    sim = m.SimulationObject(to_msm_params(ps[0]), n_streams=3, coupling=m.COUPLING_SUMMED, chunk_streams=2)
+    for i, a in enumerate(psi0s):
+        sim.set_psi(i, a)
+    for _ in range(4):
+        sim.update()
+        ens.update()
+        assert abs(sim.state(1).dt - ens.head.last_dt) <= 1e-13 * ens.head.last_dt
+    for i in range(3):
+        assert rel_l2(sim.get_psi(i), ens.streams[i].psi) < 1e-10
     sim.close()
 
 
