@@ -157,6 +157,11 @@ int msm_get_potential(msm_ctx* ctx, int32_t stream, double* phi /* n^dims */);
 int msm_step(msm_ctx* ctx, const int32_t* active, const double* drift_coeff, const double* kick_coeff,
              double* alias_mass);
 int msm_read_alias(msm_ctx* ctx, double* alias_mass);
+/* MAX of one host scalar over the ranks of the communicator (in place; a no-op without one).  The summed-density mode
+ * uses it to agree on the largest alias mass: the streams share one potential, so when any stream on any rank crosses
+ * alias_threshold every rank must stop at the same step (the reference panics, :607-617) -- otherwise the ranks would
+ * disagree about the next collective. */
+int msm_allreduce_max(msm_ctx* ctx, double* value);
 int msm_synchronize(msm_ctx* ctx);
 
 /* Stand-alone unitary FFT of `batch` host arrays (utils/fft.rs:6-98 forward / inverse, scale size^(-dims/2) in both

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "msm_get_potential": (C.c_int, [_vp, C.c_int32, _dp]),
     "msm_step": (C.c_int, [_vp, _ip, _dp, _dp, _dp]),
     "msm_read_alias": (C.c_int, [_vp, _dp]),
+    "msm_allreduce_max": (C.c_int, [_vp, _dp]),
     "msm_synchronize": (C.c_int, [_vp]),
     "msm_fft": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "msm_spec_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp]),

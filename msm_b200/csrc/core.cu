@@ -2301,6 +2301,24 @@ int msm_ensemble_accumulate(msm_ctx* ctx, const int32_t* active) {
     return MSM_OK;
 }
 
+int msm_allreduce_max(msm_ctx* ctx, double* value) {
+    if (!ctx || !value) return fail(ctx, MSM_E_ARG, "msm_allreduce_max: bad argument");
+    if (ctx->cfg.nranks <= 1 || !ctx->comm) return MSM_OK;
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int NCCL_MAX = 2;   // ncclMax
+    ctx->h_scal[0] = *value;  // mapped pinned memory: the device reads it directly
+    k_publish<<<1, 32, 0, ctx->st>>>(ctx->h_scal, ctx->scratch_small, 1);
+    CU(cudaGetLastError());
+    const int rc = g_nccl.AllReduce(ctx->scratch_small, ctx->scratch_small, 1, NCCL_DOUBLE, NCCL_MAX, ctx->comm, ctx->st);
+    if (rc != 0)
+        return fail(ctx, MSM_E_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    k_publish<<<1, 32, 0, ctx->st>>>(ctx->scratch_small, ctx->h_scal, 1);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->st));
+    *value = ctx->h_scal[0];
+    return MSM_OK;
+}
+
 int msm_ensemble_allreduce(msm_ctx* ctx) {
     if (!ctx) return MSM_E_ARG;
     if (!ctx->ens_psi) return fail(ctx, MSM_E_STATE, "msm_ensemble_allreduce: call msm_ensemble_accumulate first");

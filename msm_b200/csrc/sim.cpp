@@ -547,6 +547,18 @@ static int update_streams(msm_sim* sim, const int32_t* subset) {
         sim->err = msm_last_error(sim->ctx);
         return rc;
     }
+    // Summed density: the streams of ALL ranks share one potential, so an alias event anywhere stops every stream at this
+    // step (the reference would have panicked, :607-617); the ranks agree on the largest alias mass first.
+    double alias_worst = 0.0;
+    if (summed) {
+        for (int s = 0; s < S; ++s)
+            if (active[s]) alias_worst = fmax(alias_worst, alias[s]);
+        rc = msm_allreduce_max(sim->ctx, &alias_worst);
+        if (rc) {
+            sim->err = msm_last_error(sim->ctx);
+            return rc;
+        }
+    }
     int result = MSM_OK;
     for (int s = 0; s < S; ++s) {
         if (!active[s]) continue;
@@ -554,12 +566,13 @@ static int update_streams(msm_sim* sim, const int32_t* subset) {
         st = next[s];
         if (!p.expanding) st.time = st.time + dts[s];                            // :590
         st.alias_mass = alias[s];
-        st.aliased = alias[s] > p.alias_threshold ? 1 : 0;                       // :1288
+        st.aliased = (alias[s] > p.alias_threshold || (summed && alias_worst > p.alias_threshold)) ? 1 : 0;   // :1288
         if (st.aliased) {
             result = MSM_E_ALIASING;                                             // the reference panics here (:607-617)
-            char buf[160];
-            snprintf(buf, sizeof buf, "simulation aliased: stream %d threshold %g k2_cutoff %g p_mass %g", s,
-                     p.alias_threshold, p.k2_cutoff, alias[s]);
+            char buf[200];
+            snprintf(buf, sizeof buf, "simulation aliased: stream %d threshold %g k2_cutoff %g p_mass %g%s", s,
+                     p.alias_threshold, p.k2_cutoff, alias[s],
+                     alias[s] > p.alias_threshold ? "" : " (another stream of the summed ensemble crossed the threshold)");
             sim->err = buf;
         }
         if (dump[s]) {                                                           // :620-631 / :828-844

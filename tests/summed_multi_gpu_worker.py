@@ -66,6 +66,29 @@ for name, per_rank, size, chunk, slabs in (("spherical-tophat", 3, None, 0, None
         sys.exit(1)
 os.environ.pop("MSM_B200_AR_SLABS", None)
 
+# an alias event on ONE rank stops the whole summed ensemble at the same step on EVERY rank (msm_allreduce_max)
+p_alias = gu.oracle_streams("spherical-tophat", limit=1)[0]
+p_alias.alias_threshold = 1e-6
+good = gu.initial_wavefunction(p_alias)
+rng = np.random.default_rng(3)
+noisy = o.normalize(rng.standard_normal(good.shape) + 1j * rng.standard_normal(good.shape), p_alias.dx, 3)   # alias mass ~ 3.5e-5, the smooth stream ~ 1e-12
+sim = m.SimulationObject(gu.to_msm_params(p_alias), n_streams=1, coupling=m.COUPLING_SUMMED, device=local, rank=rank,
+                         nranks=world, n_streams_global=world, nccl_unique_id=fresh_unique_id())
+sim.set_psi(0, noisy if rank == 0 else good)
+try:
+    sim.update()
+    stopped = False
+except m.FourierAliasing:
+    stopped = True
+ok = stopped and sim.state(0).aliased == 1 and not sim.not_finished()
+print(f"rank {rank} alias on rank 0 only: update raised FourierAliasing = {stopped}, own alias mass {sim.state(0).alias_mass:.3e} -> {'OK' if ok else 'FAIL'}", flush=True)
+sim.close()
+t = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+dist.all_reduce(t)
+if int(t.item()) != 0:
+    dist.destroy_process_group()
+    sys.exit(1)
+
 # ensemble statistics over ALL streams: per-rank accumulation + ncclAllReduce of the four grids inside
 # the library, against the restatement of the synthesizer (synthesizer/src/lib.rs:106-342) on the host
 from msm_b200 import driver

@@ -34,4 +34,4 @@ def test_summed_mode_on_two_ranks_matches_the_oracle_ensemble():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     sys.stdout.write(out.stdout)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert out.stdout.count("-> OK") >= 12 and "FAIL" not in out.stdout
+    assert out.stdout.count("-> OK") >= 14 and "FAIL" not in out.stdout
