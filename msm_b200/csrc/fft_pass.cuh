@@ -500,6 +500,15 @@ template <int N, int LOP, int SOP, bool XL> constexpr int kernel_minb() {
     if (EV == Plan<N>::E && XL && tile_T<N, XL>() != Plan<N>::T && !uses_dtab(LOP, SOP)) return MSM_XL_MINB_NODT * (N == 256 ? 2 : 1);
     return tile_minb<N, XL, EV>();
 }
+// Register double buffering (contiguous-axis kernels with plain loads): the next item's elements are loaded into a
+// second register set while the current item is transformed, so that a CTA's critical path per item is its butterflies
+// and exchanges, not load latency + butterflies (these kernels run 4 CTAs of 128 threads per SM with 128 registers).
+#ifndef MSM_RP
+#define MSM_RP 0
+#endif
+template <int N, int LOP, int SOP, bool XL> constexpr bool reg_prefetch() {
+    return MSM_RP && XL && tile_T<N, XL>() != Plan<N>::T && (LOP == L_NONE || LOP == L_DRIFT) && plan_E<N, LOP, SOP, XL>() == 8;
+}
 template <int N, int LOP, int SOP> constexpr int table_elems() {   // double2 units
     return (kTwSmem ? N : 0) + (sop_needs_k2(SOP) ? N / 2 + 1 : 0) + (uses_dtab(LOP, SOP) ? 2 * N : 0) +
            (uses_wreal(LOP, SOP) ? N : 0);
@@ -607,6 +616,25 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     // the host makes tiles_per_cta a divisor of tiles_inner: consecutive tiles of one CTA differ by inner_stride
     const int tstride = (int)p.inner_stride, loff = la * (int)p.lstride;
     int origin = tile_origin(p.tile0 + blockIdx.x * p.tiles_per_cta) - tstride;
+    constexpr bool RP = reg_prefetch<N, LOP, SOP, XL>();
+    [[maybe_unused]] double2 nxt[RP ? E : 1];
+    [[maybe_unused]] bool have_nxt = false;
+    // the item after (ti_, q_) in this CTA's walk: partner stream of the same tile, else first stream of the next tile
+    auto next_item = [&](int ti_, int q_, int origin_, int& ti2, int& q2, int& origin2) -> bool {
+        if (q_ + 1 < p.gsz && g * p.gsz + q_ + 1 < p.ns) {
+            ti2 = ti_, q2 = q_ + 1, origin2 = origin_;
+            return true;
+        }
+        if (ti_ + 1 < p.tiles_per_cta && p.tile0 + blockIdx.x * p.tiles_per_cta + ti_ + 1 < p.tile_end) {
+            ti2 = ti_ + 1, q2 = 0, origin2 = origin_ + tstride;
+            return true;
+        }
+        return false;
+    };
+    auto item_src = [&](int q_, int origin_) -> const double2* {
+        const int li_ = g * p.gsz + q_;
+        return p.src + (long long)(p.src_by_sid ? p.sid[li_] : li_) * p.src_sstride + origin_;
+    };
     for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
     const int tile = p.tile0 + blockIdx.x * p.tiles_per_cta + ti;
     if (tile >= p.tile_end) break;
@@ -694,14 +722,14 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
 
         // pull the NEXT item (partner stream of this tile, else first stream of the next tile) into L2 now, so its
         // loads find the data on chip: DRAM stays busy while this item computes
+        int ti1 = 0, q1 = 0, origin1 = 0, ti2 = 0, q2 = 0, origin2 = 0;
+        const bool has1 = next_item(ti, q, origin, ti1, q1, origin1);
         if (p.l2_prefetch && (p.tiles_per_cta > 1 || p.gsz > 1)) {
-            const bool same_tile = !last_of_group;
-            const int nli = same_tile ? li + 1 : g * p.gsz;
-            if (same_tile || (tile + 1 < p.ntiles && ti + 1 < p.tiles_per_cta)) {
-                const int ns_ = p.sid[nli];
-                const int norigin = same_tile ? origin : origin + tstride;
-                prefetch_tile(p.src + (long long)(p.src_by_sid ? ns_ : nli) * p.src_sstride + norigin);
-                if ((LOP == L_KICK || LOP == L_KICK_IX) && !same_tile) prefetch_tile(pb + norigin);
+            if constexpr (RP) {   // the next item goes to registers (below): L2 gets the one after it
+                if (has1 && next_item(ti1, q1, origin1, ti2, q2, origin2)) prefetch_tile(item_src(q2, origin2));
+            } else if (has1) {
+                prefetch_tile(item_src(q1, origin1));
+                if ((LOP == L_KICK || LOP == L_KICK_IX) && ti1 != ti) prefetch_tile(pb + origin1);
             }
         }
 
@@ -730,11 +758,33 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             }
         }
         // ---- load (stage-0 input order): all global loads first, operators afterwards ----
+        if constexpr (RP) {
+            if (have_nxt) {
 #pragma unroll
-        for (int c = 0; c < NB0; ++c) {
+                for (int i = 0; i < E; ++i) v[i] = nxt[i];
+            } else {
 #pragma unroll
-            for (int n = 0; n < R0; ++n) {
-                v[c * R0 + n] = src[eoff(c + n * NB0)];
+                for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                    for (int n = 0; n < R0; ++n) v[c * R0 + n] = src[eoff(c + n * NB0)];
+                }
+            }
+            have_nxt = has1;
+            if (has1) {   // in flight while this item is transformed
+                const double2* __restrict__ nsrc = item_src(q1, origin1) + loff;
+#pragma unroll
+                for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                    for (int n = 0; n < R0; ++n) nxt[c * R0 + n] = nsrc[a0 + (c + n * NB0) * astep];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NB0; ++c) {
+#pragma unroll
+                for (int n = 0; n < R0; ++n) {
+                    v[c * R0 + n] = src[eoff(c + n * NB0)];
+                }
             }
         }
         if constexpr (LOP == L_DRIFT) {
