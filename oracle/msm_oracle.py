@@ -18,13 +18,22 @@ PINNING STATUS
   unitary FFT normalisation + invertibility (simulator/tests/fft.rs:2-64 and the other 11
   round trips), `normalize` (utils/grid.rs:107-186), `parse_seeds` (common/src/parameters.rs:121-144),
   TOML parsing of the shipped example files, npz IC fixture loading.
-* PARITY UNPINNED for: the integrator step (`update`, `calculate_potential`, `get_timestep`,
-  `check_alias`), the sampler's random stream (ArrayFire Philox -> normal is not reproducible
-  without ArrayFire; the Poisson scheme is unseeded in the reference, ics.rs:497) and the scale
-  factor a(t) (crate `cosmology` 0.2.0 is not vendored).  The reference holds no golden data
-  for any of these (its tests never call `update`), and the reference itself cannot be built here
-  (no cargo/rustc, ArrayFire 3.8.0 binary is downloaded by simulator/build.rs:10-11).  For these the
-  oracle is a line-by-line restatement, nothing more.
+* pinned against the reference's own LEGACY PYTHON integrator, executed in the build container
+  (tests/golden/make_legacy_golden.py -> tests/golden/legacy_grav3d_traj.npz): `Grav3D.Update` +
+  `compute_phi` of python_deprecated/gravSolver.py:77-118 is the authors' earlier implementation of
+  the same static-box split step (half drift, density, Poisson solve with phi_k[0] = 0, full kick,
+  half drift) with a fixed dt.  `SimulationObject.update` / `calculate_potential` agree with that
+  run to 2.5e-16 after 1 step and 5e-14 after 40 steps of a collapsing Gaussian (kick phase
+  0.45 rad per step), phi to 1.5e-16 (test_integrator_step_matches_the_reference_legacy_python_run).
+  This pins the drift / kick phases, the density prefactor, the Poisson constant, sign and DC
+  handling, the transform conventions and the order of operations of the static-box step.
+* PARITY UNPINNED for: the adaptive time step and dump bookkeeping (`get_timestep`), `check_alias`
+  (the legacy code normalises differently), the expanding-box step, the sampler's random stream
+  (ArrayFire Philox -> normal is not reproducible without ArrayFire; the Poisson scheme is unseeded
+  in the reference, ics.rs:497) and the scale factor a(t) (crate `cosmology` 0.2.0 is not
+  vendored).  The reference holds no golden data for any of these (its Rust tests never call
+  `update`), and the Rust crate cannot be built here (no cargo/rustc, ArrayFire 3.8.0 binary is
+  downloaded by simulator/build.rs:10-11).  For these the oracle is a line-by-line restatement.
 
 Third-party code the reference's arithmetic lives in (un-vendored):
   arrayfire crate =3.8.0 + ArrayFire v3.8.0 binary (simulator/Cargo.toml:14, build.rs:10-11)

@@ -1,11 +1,13 @@
 """Pins the oracle against every golden value the reference's own tests hold for this path,
 plus closed-form known answers for the operators the reference never tests (drift, Poisson)."""
 import math
+import os
 
 import numpy as np
 import pytest
 
 from oracle import msm_oracle as o
+from conftest import rel_l2
 from golden_util import GOLDEN, load_toml
 
 
@@ -223,3 +225,34 @@ def test_synthesizer_combine_known_answers():
     c = o.synthesizer_combine([psi, -psi], dv)
     assert np.max(np.abs(c["psi"])) == 0.0
     assert abs(c["Qx"] - np.sum(np.abs(psi) ** 2) * dv) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the integrator step against the reference's own legacy Python integrator (python_deprecated/gravSolver.py)
+# ---------------------------------------------------------------------------------------------------------------
+def legacy_parameters():
+    """tests/golden/legacy_grav3d_traj.npz: `Grav3D.Update` of /root/reference/python_deprecated/gravSolver.py:91-118 run
+    in the build container (tests/golden/make_legacy_golden.py): fixed dt = 0.2, psi after 1 / 10 / 40 steps.  The
+    oracle takes the same dt when the dump interval is the binding constraint (cfl huge, final_time / dumps = dt)."""
+    z = np.load(os.path.join(GOLDEN, "legacy_grav3d_traj.npz"))
+    n, length, hbar_, mtot, c, dt = z["params"]
+    assert c == o.POIS_CONST
+    p = o.SimulationParameters(axis_length=float(length), time=0.0, final_sim_time=float(dt) * 40, cfl=1e9, num_data_dumps=40,
+                               total_mass=float(mtot), particle_mass=o.HBAR / float(hbar_), sim_name="legacy",
+                               k2_cutoff=0.95, alias_threshold=1e9, hbar_=float(hbar_), dims=3, size=int(n))
+    return z, p, float(dt)
+
+
+def test_integrator_step_matches_the_reference_legacy_python_run():
+    """Pins drift, density, Poisson solve (constant, sign, k = 0 -> 0), kick and their order in `SimulationObject.update`
+    (restating simulation_object.rs:504-581, :1031-1110) to code written by the reference's authors and EXECUTED here:
+    1 step 2.5e-16, 40 steps of a collapsing Gaussian (kick phase 0.45 rad per step) 5e-14."""
+    z, p, dt = legacy_parameters()
+    sim = o.SimulationObject(p, z["psi0"])
+    sim.calculate_potential()
+    assert rel_l2(sim.phi.real, z["phi0"]) < 1e-14
+    for k in range(1, 41):
+        sim.update()
+        assert abs(sim.last_dt - dt) <= 1e-15                      # dump-limited: exactly the legacy run's fixed dt
+        if k in (1, 10, 40):
+            assert rel_l2(sim.psi, z[f"psi_{k:03d}"]) < (1e-14 if k == 1 else 1e-12), k
