@@ -27,6 +27,9 @@ PINNING STATUS
   0.45 rad per step), phi to 1.5e-16 (test_integrator_step_matches_the_reference_legacy_python_run).
   This pins the drift / kick phases, the density prefactor, the Poisson constant, sign and DC
   handling, the transform conventions and the order of operations of the static-box step.
+  (The legacy tree also corroborates the sampler FORMULAS -- python_deprecated/testSinWaveCollapse.py:113-129 adds
+  sqrt(.5/n) (N(0, 1/2) + i N(0, 1/2)) for Wigner and sqrt(2) times that for Husimi, i.e. the (N + iN) / (2 sqrt n)
+  and (N + iN) / (sqrt 2 sqrt n) of ics.rs:578-585 / :622-629 -- but not a random stream.)
 * PARITY UNPINNED for: the adaptive time step and dump bookkeeping (`get_timestep`), `check_alias`
   (the legacy code normalises differently), the expanding-box step, the sampler's random stream
   (ArrayFire Philox -> normal is not reproducible without ArrayFire; the Poisson scheme is unseeded
