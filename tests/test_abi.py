@@ -111,7 +111,10 @@ def test_no_store_backedge_hazard_in_the_built_kernels():
     import sys
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not available")
-    objs = sorted(glob.glob(os.path.join(ROOT, "msm_b200", "csrc", "build", "fft_*.o")))
+    objs = sorted(glob.glob(os.path.join(ROOT, "msm_b200", "csrc", "build", "fft_*.o")))   # incl. fft_tma.o
+    core = os.path.join(ROOT, "msm_b200", "csrc", "build", "core.o")
+    if os.path.exists(core):
+        objs.append(core)
     if not objs:
         pytest.skip("no kernel objects (library built elsewhere)")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_war_hazard.py")] + objs, capture_output=True, text=True)
