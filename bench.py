@@ -392,27 +392,33 @@ def main():
 
     # ---- the north-star's coupled mode beside the headline: |psi|^2 summed over ALL streams (local accumulate ->
     #      ncclAllReduce of the real density over NVLink -> replicated real-field Poisson solve), same streams, same steps
-    summed = None
-    if args.coupling == "independent" and not args.no_summed:
+    def summed_record():
         r = resident("summed")
         r["sim"].close()
         sp = r["prof"]
         per = lambda pred: sum(x["ms_total"] for x in sp if pred(x["name"])) / args.steps       # noqa: E731
         sb = alg_bytes("summed", n_local)
-        summed = {"value": r["value"], "unit": "cell-updates/s", "ms_per_step": r["ms"] / args.steps, "steps": args.steps,
-                  "allreduce_ms_per_step": per(lambda nm: nm.startswith("nccl_")),
-                  "poisson_ms_per_step": per(lambda nm: ",half>" in nm or ",nyquist>" in nm or "poisson" in nm
-                                             or nm.startswith(("pack_", "unpack_"))),
-                  "algorithmic_bytes_per_cell_update": sb,
-                  "step_frac": r["value"] / world * sb / 1e9 / (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-                                                              if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0),
-                  "gpu_launches": int(r["launches"]), "clocks": r["clk"],
-                  "what": "rho = (A/S) sum over all streams of |psi_s|^2: accumulated over the local streams inside the "
-                          "last inverse pass (real plane, 8 B/cell), ncclAllReduce of n^3 doubles in place, replicated "
-                          "real-field (R2C/C2R half-spectrum) Poisson solve; twice per step (kick potential, dt potential)",
-                  "kernels": [{"name": x["name"], "launches": x["launches"], "ms": round(x["ms_total"], 3),
-                               "GBps": round(x["algorithmic_bytes"] / (x["ms_total"] * 1e-3) / 1e9, 1)}
-                              for x in sorted(sp, key=lambda x: -x["ms_total"])]}
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm = float(json.load(open(ppath))["hbm_gbs"]) if os.path.exists(ppath) else 6650.0
+        return {"value": r["value"], "unit": "cell-updates/s", "ms_per_step": r["ms"] / args.steps, "steps": args.steps,
+                "allreduce_ms_per_step": per(lambda nm: nm.startswith("nccl_")),
+                "poisson_ms_per_step": per(lambda nm: ",half>" in nm or ",nyquist>" in nm or "poisson" in nm
+                                           or nm.startswith(("pack_", "unpack_"))),
+                "algorithmic_bytes_per_cell_update": sb, "step_frac": r["value"] / world * sb / 1e9 / hbm,
+                "gpu_launches": int(r["launches"]), "clocks": r["clk"],
+                "what": "rho = (A/S) sum over all streams of |psi_s|^2: accumulated over the local streams inside the "
+                        "last inverse pass (real plane, 8 B/cell), ncclAllReduce of n^3 doubles in place, replicated "
+                        "real-field (R2C/C2R half-spectrum) Poisson solve; twice per step (kick potential, dt potential)",
+                "kernels": [{"name": x["name"], "launches": x["launches"], "ms": round(x["ms_total"], 3),
+                             "GBps": round(x["algorithmic_bytes"] / (x["ms_total"] * 1e-3) / 1e9, 1)}
+                            for x in sorted(sp, key=lambda x: -x["ms_total"])]}
+
+    summed = None
+    if args.coupling == "independent" and not args.no_summed:
+        try:
+            summed = summed_record()
+        except Exception as exc:      # the headline line must survive a failure of the side record
+            summed = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_e2e:
         sim = m.SimulationObject(params, n_streams=n_local, device=device, chunk_streams=chunk, coupling=coupling,
                                  **comm_kwargs())
