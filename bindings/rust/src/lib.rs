@@ -110,6 +110,7 @@ extern "C" {
     pub fn msm_sim_dump(sim: *mut MsmSim, stream: i32, root: *const c_char, name: *const c_char, idx: u32) -> c_int;
     pub fn msm_sim_dump_potential(sim: *mut MsmSim, stream: i32, root: *const c_char, name: *const c_char, idx: u32) -> c_int;
     pub fn msm_sim_wait_io(sim: *mut MsmSim) -> c_int;
+    pub fn msm_sim_reserve_dump_buffers(sim: *mut MsmSim, n: i32) -> c_int;
     pub fn msm_sim_run_streams_seeded(sim: *mut MsmSim, n: i32, streams: *const i32, scheme: i32, seeds: *const u64,
                                       re_out: *const *mut f64, im_out: *const *mut f64, max_updates: u64) -> c_int;
     // grid level, for hosts that keep get_timestep / the scale-factor solver in Rust

@@ -326,6 +326,10 @@ int msm_sim_dump_potential(msm_sim* sim, int32_t stream, const char* root_dir, c
  * `expect("write to disk failed")`) makes the next msm_sim_dump* or msm_sim_wait_io return MSM_E_IO.
  * msm_sim_wait_io joins the background NPY writers (the reference joins its I/O threads when a stream finishes, :651-655). */
 int msm_sim_wait_io(msm_sim* sim);
+/* Pin up to n staging buffers of the dump pipeline now (2 * n^dims doubles each; the pool is capped by
+ * MSM_B200_DUMP_BUFFERS, default 4).  Pinning costs 0.5-1 s per GiB; without this call the pool grows on demand, i.e.
+ * inside the step loop at the first dumps. */
+int msm_sim_reserve_dump_buffers(msm_sim* sim, int32_t n);
 
 /* host scalars, exported for the parity tests of rows a7/a8/a16 */
 double msm_get_tau(double target_time, double omega_matter_now, double omega_radiation_now, double h, double z0,

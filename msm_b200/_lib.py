@@ -133,6 +133,7 @@ PROTOTYPES = {
     "msm_sim_dump": (C.c_int, [_vp, C.c_int32, C.c_char_p, C.c_char_p, C.c_uint32]),
     "msm_sim_dump_potential": (C.c_int, [_vp, C.c_int32, C.c_char_p, C.c_char_p, C.c_uint32]),
     "msm_sim_wait_io": (C.c_int, [_vp]),
+    "msm_sim_reserve_dump_buffers": (C.c_int, [_vp, C.c_int32]),
     "msm_get_tau": (C.c_double, [C.c_double] * 6 + [C.c_int32]),
     "msm_supercomoving_boxsize": (C.c_double, [C.c_double] * 5),
     "msm_scale_factor_after": (C.c_double, [C.c_double] * 6),

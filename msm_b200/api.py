@@ -460,6 +460,10 @@ class SimulationObject:
         check(lib.msm_sim_dump_potential(self.handle, stream, root_dir.encode(), sim_name.encode(), dump_index),
               self.handle, sim=True)
 
+    def reserve_dump_buffers(self, n: int) -> None:
+        """pin n staging buffers of the dump pipeline up front (otherwise the pool grows at the first dumps)"""
+        check(lib.msm_sim_reserve_dump_buffers(self.handle, int(n)), self.handle, sim=True)
+
     def wait_io(self) -> None:
         check(lib.msm_sim_wait_io(self.handle), self.handle, sim=True)
 

@@ -264,17 +264,31 @@ int pool_error(msm_sim* sim) {
     return MSM_E_IO;
 }
 
-// a free staging buffer; grows the pool up to MSM_B200_DUMP_BUFFERS (default 4), then waits for a writer to finish
-int pool_acquire(msm_sim* sim, double** out) {
-    DumpPool& P = sim->pool;
+size_t pool_cap() {
     size_t cap = 4;
     if (const char* e = getenv("MSM_B200_DUMP_BUFFERS")) cap = (size_t)std::max(1, atoi(e));
+    return cap;
+}
+
+// A free staging buffer; grows the pool up to MSM_B200_DUMP_BUFFERS (default 4), then waits for a writer to finish.
+// Pinning host memory is expensive (cudaMallocHost: 0.1-0.2 s per 256 MiB measured), so once the pool holds two buffers
+// a momentary shortage first waits 20 ms for a writer before it pays for another buffer; msm_sim_reserve_dump_buffers
+// moves the whole cost in front of the step loop.
+int pool_acquire(msm_sim* sim, double** out) {
+    DumpPool& P = sim->pool;
+    const size_t cap = pool_cap();
     std::unique_lock<std::mutex> lock(P.mu);
+    bool waited = false;
     for (;;) {
         if (!P.free_.empty()) {
             *out = P.free_.back();
             P.free_.pop_back();
             return MSM_OK;
+        }
+        if (P.all.size() >= 2 && P.all.size() < cap && !waited) {
+            waited = true;
+            P.cv.wait_for(lock, std::chrono::milliseconds(20));
+            continue;
         }
         if (P.all.size() < cap) {
             void* p = nullptr;
@@ -775,13 +789,22 @@ static int dump_field(msm_sim* sim, int32_t stream, const char* root_dir, const 
     if (!sim || !root_dir || !sim_name || stream < 0 || stream >= sim->p.n_streams)
         return sfail(sim, MSM_E_ARG, "msm_sim_dump: bad argument");
     if (int rc = pool_error(sim)) return rc;
+    const bool trace = getenv("MSM_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        fprintf(stderr, "[msm_sim_dump] %8.2f ms  %s\n", ms, what);
+    };
     // at most 2 * MAX_CONCURRENT_GRID_WRITES live writers (simulation_object.rs:39,:1123)
     if (sim->io.size() >= 32)
         if (int rc = msm_sim_wait_io(sim)) return rc;
     const std::string dir = std::string(root_dir) + "/" + sim_name;
     if (!mkdirs(dir)) return sfail(sim, MSM_E_IO, "dump: cannot create directory " + dir + ": " + strerror(errno));   // :1119
+    stamp("directory ready");
     double* buf = nullptr;
     if (int rc = pool_acquire(sim, &buf)) return rc;
+    stamp("staging buffer acquired");
     const size_t cells = sim_cells(sim);
     uint64_t ticket = 0;
     int rc;
@@ -798,8 +821,34 @@ static int dump_field(msm_sim* sim, int32_t stream, const char* root_dir, const 
     }
     char base[64];
     snprintf(base, sizeof base, "/%s_%05u", potential ? "potential" : "psi", dump_index);   // :1155-1158, :1171-1174
+    stamp("transfer enqueued");
     spawn_writers(sim, buf, !potential, ticket, dir + base + "_real", dir + base + "_imag", potential);   // io.rs:54-55
+    stamp("writers started");
     return MSM_OK;
+}
+
+int msm_sim_reserve_dump_buffers(msm_sim* sim, int32_t n) {
+    if (!sim || n < 0) return sfail(sim, MSM_E_ARG, "msm_sim_reserve_dump_buffers: bad argument");
+    DumpPool& P = sim->pool;
+    const size_t want = std::min<size_t>((size_t)n, pool_cap());
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> lock(P.mu);
+            if (P.all.size() >= want) return MSM_OK;
+        }
+        void* p = nullptr;
+        const int rc = msm_host_alloc(sim->ctx, 2 * sizeof(double) * sim_cells(sim), &p);
+        if (rc) {
+            sim->err = msm_last_error(sim->ctx);
+            return rc;
+        }
+        {
+            std::lock_guard<std::mutex> lock(P.mu);
+            P.all.push_back((double*)p);
+            P.free_.push_back((double*)p);
+        }
+        P.cv.notify_all();
+    }
 }
 
 int msm_sim_dump(msm_sim* sim, int32_t stream, const char* root_dir, const char* sim_name, uint32_t dump_index) {
