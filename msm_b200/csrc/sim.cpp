@@ -22,6 +22,7 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -336,8 +337,18 @@ void spawn_writers(msm_sim* sim, double* buf, bool has_ticket, uint64_t ticket, 
         else if (!write_npy(path, data, dims, n)) pool_fail(sim, "dump: cannot write " + path + ": " + strerror(errno));
         if (left->fetch_sub(1) == 1) pool_release(sim, buf);
     };
-    sim->io.emplace_back(job, path_re, (const double*)buf);
-    sim->io.emplace_back(job, path_im, imag_zero ? (const double*)nullptr : (const double*)(buf + cells));
+    const double* im_plane = imag_zero ? (const double*)nullptr : (const double*)(buf + cells);
+    // a thread that cannot be started (std::system_error) must not unwind through the C ABI: its plane is written here
+    try {
+        sim->io.emplace_back(job, path_re, (const double*)buf);
+    } catch (const std::exception&) {
+        job(path_re, (const double*)buf);
+    }
+    try {
+        sim->io.emplace_back(job, path_im, im_plane);
+    } catch (const std::exception&) {
+        job(path_im, im_plane);
+    }
 }
 
 }  // namespace
