@@ -199,6 +199,7 @@ def run_both(ps, steps, coupling=m.COUPLING_INDEPENDENT, chunk=0, psi0s=None):
     ("spherical-tophat", 32, 2, 6), ("spherical-tophat", 64, 2, 4), ("gaussian-overdensity-mft", 64, 1, 4),
     ("repro-planeWave1d", None, 3, 8), ("spherical-tophat", 4, 2, 3), ("spherical-tophat", 8, 3, 3),
     ("spherical-tophat", 64, 3, 3), ("spherical-tophat", 128, 3, 2),      # several tiles per CTA, a one-stream group
+    ("spherical-tophat-cosmo", 64, 3, 4), ("spherical-tophat-cosmo", 128, 2, 2),  # expanding box beyond 16^3
 ])
 def test_trajectory_matches_oracle(name, size, nstreams, steps):
     ps = oracle_streams(name, size, limit=nstreams)
