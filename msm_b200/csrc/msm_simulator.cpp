@@ -194,6 +194,7 @@ int main(int argc, char** argv) {
         return rc_;
     };
     if (!test_only) {
+        CHECK_SIM(msm_sim_reserve_dump_buffers(sim, 2));                                                 // pinned staging, up front
         for (int s = 0; s < S; ++s) CHECK_SIM(dump(s, 0));                                               // main.rs:61
         long updates = 0;
         while (msm_sim_not_finished(sim) && (max_updates < 0 || updates < max_updates)) {               // main.rs:65

@@ -66,6 +66,7 @@ def run(cfg: RunConfig, out_root: str = "sim-data", rank: int = 0, nranks: int =
             sim.dump_potential(li, out_root, cfg.streams[s].sim_name, index)
 
     if write:
+        sim.reserve_dump_buffers(2)                                  # pin the dump staging before the loop, not inside it
         for li, s in enumerate(local):                               # main.rs:61 dump the initial condition
             dump(li, s, 0)
     updates = 0
