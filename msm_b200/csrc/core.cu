@@ -498,6 +498,7 @@ struct msm_ctx {
     int tiles_per_cta = 4;   // consecutive tiles per CTA of the one-tile kernel; next item is prefetched into L2
     int tiles_per_cta_x = 16;  // the same for the small tiles of the contiguous axis
     int tiles_per_cta_fused = 4;   // multiplier of tiles_per_cta for the strided two-transform kernels (MSM_B200_TPCF)
+    int interleave = 1;            // MSM_B200_ILV: neighbouring CTAs interleave their tiles on the strided axes
     int num_sms = 148;
 };
 
@@ -760,6 +761,11 @@ int run_passes(msm_ctx* ctx, const std::vector<PassSpec>& seq, const int* ids, i
         const int walk = xl ? ctx->tiles_per_cta_x
                             : ctx->tiles_per_cta * ((sop == S_POISSON_INV || sop == S_DRIFT_ALIAS_IZ) ? ctx->tiles_per_cta_fused : 1);
         p.tiles_per_cta = (int)std::__gcd((long long)walk, (long long)g.tiles_inner);
+        // interleaved walk of W neighbouring CTAs (strided axes only; whole launches only; W * tiles_per_cta must tile a row)
+        p.interleave = 1;
+        if (!xl && ctx->interleave > 1 && seq[k].tile0 == 0 && seq[k].tile_end < 0 &&
+            g.tiles_inner % (ctx->interleave * p.tiles_per_cta) == 0)
+            p.interleave = ctx->interleave;
         if (p.tile0 % p.tiles_per_cta) p.tiles_per_cta = (int)std::__gcd((long long)p.tiles_per_cta, (long long)p.tile0);
         p.l2_prefetch = ctx->l2_prefetch;
         if (sop_is_alias(sop))
@@ -1154,6 +1160,7 @@ int msm_create(const msm_config* cfg, msm_ctx** out) {
     if (const char* e = getenv("MSM_B200_TPC")) ctx->tiles_per_cta = std::max(1, atoi(e));
     if (const char* e = getenv("MSM_B200_TPCX")) ctx->tiles_per_cta_x = std::max(1, atoi(e));
     if (const char* e = getenv("MSM_B200_TPCF")) ctx->tiles_per_cta_fused = std::max(1, atoi(e));
+    if (const char* e = getenv("MSM_B200_ILV")) ctx->interleave = std::max(1, atoi(e));
     ctx->lb = (cfg->dims == 3 && n >= 512) ? 4 : 0;
     if (const char* e = getenv("MSM_B200_LB")) ctx->lb = (cfg->dims == 3 && (1 << atoi(e)) <= n) ? std::max(0, atoi(e)) : 0;
     // the pass kernels address a thread's elements e = t + NT * j (NT = n / 8 threads per line) as a0 + j * step,

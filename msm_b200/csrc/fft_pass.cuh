@@ -97,6 +97,7 @@ struct PassParams {
     const double2* wreal;                 // W_2N^k = exp(-2 pi i k / 2N), k < N
     int tile0, tile_end;                  // this launch covers tiles [tile0, tile_end) (slab-pipelined launches)
     int tiles_per_cta;                    // one-tile kernel: consecutive tiles walked by one CTA (L2 prefetch depth)
+    int interleave;                       // W: CTAs b, b+1, .. b+W-1 interleave their tiles (1 = each walks its own run)
     int zero;                             // always 0; only the compiler does not know (see data_dependent)
     int l2_prefetch;                      // pull the next item's tile into L2 while the current one computes
 };
@@ -614,8 +615,13 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
     };
 
     // the host makes tiles_per_cta a divisor of tiles_inner: consecutive tiles of one CTA differ by inner_stride
-    const int tstride = (int)p.inner_stride, loff = la * (int)p.lstride;
-    int origin = tile_origin(p.tile0 + blockIdx.x * p.tiles_per_cta) - tstride;
+    // Tile walk.  W = p.interleave CTAs with consecutive block indices share a run of W * tiles_per_cta adjacent tiles and
+    // take every W-th one: CTAs that were launched together read ADJACENT 128-byte segments of the same rows at about the
+    // same time (DRAM row locality), instead of each CTA walking its own 4 adjacent tiles one after the other.
+    const int W = p.interleave > 0 ? p.interleave : 1;
+    const int first_tile = p.tile0 + (blockIdx.x / W) * (W * p.tiles_per_cta) + blockIdx.x % W;
+    const int tstride = W * (int)p.inner_stride, loff = la * (int)p.lstride;
+    int origin = tile_origin(first_tile) - tstride;
     constexpr bool RP = reg_prefetch<N, LOP, SOP, XL>();
     [[maybe_unused]] double2 nxt[RP ? E : 1];
     [[maybe_unused]] bool have_nxt = false;
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
             ti2 = ti_, q2 = q_ + 1, origin2 = origin_;
             return true;
         }
-        if (ti_ + 1 < p.tiles_per_cta && p.tile0 + blockIdx.x * p.tiles_per_cta + ti_ + 1 < p.tile_end) {
+        if (ti_ + 1 < p.tiles_per_cta && first_tile + (ti_ + 1) * W < p.tile_end) {
             ti2 = ti_ + 1, q2 = 0, origin2 = origin_ + tstride;
             return true;
         }
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(tile_threads<N, XL, plan_E<N, LOP, SOP, XL>()>
         return p.src + (long long)(p.src_by_sid ? p.sid[li_] : li_) * p.src_sstride + origin_;
     };
     for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
-    const int tile = p.tile0 + blockIdx.x * p.tiles_per_cta + ti;
+    const int tile = first_tile + ti * W;
     if (tile >= p.tile_end) break;
     origin += tstride;
     const int base = origin + loff;
